@@ -1,0 +1,285 @@
+// api.cu - the C-ABI entry points that chain the kernels (include/ast_frontend.h).
+#include <cmath>
+
+#include "common.cuh"
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace ast {
+
+// ---- diagnostic profiler ---------------------------------------------------------------------
+struct ProfileRecord {
+  const char* name;
+  cudaEvent_t begin, end;
+};
+static bool g_profile_on = false;
+static std::vector<ProfileRecord> g_profile;
+
+bool profile_on() { return g_profile_on; }
+
+void profile_mark(const char* name, cudaStream_t st, bool begin) {
+  if (begin) {
+    ProfileRecord r;
+    r.name = name;
+    cudaEventCreate(&r.begin);
+    cudaEventCreate(&r.end);
+    cudaEventRecord(r.begin, st);
+    g_profile.push_back(r);
+  } else {
+    for (size_t i = g_profile.size(); i-- > 0;)
+      if (g_profile[i].name == name) {
+        cudaEventRecord(g_profile[i].end, st);
+        break;
+      }
+  }
+}
+
+static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+  float2* stats_table;  // batch * 2 * 597 (mean, rstd)
+  float* octaves;       // batch * cqt_ws_clip_stride floats
+  size_t used;
+};
+
+static size_t stats_table_bytes(int batch) { return align_up(sizeof(float2) * 2 * kFTotal * (size_t)(batch > 0 ? batch : 1)); }
+static size_t octave_bytes(int batch, long long max_samples) {
+  return align_up(sizeof(float) * (size_t)cqt_ws_clip_stride(max_samples) * (size_t)batch);
+}
+
+static int carve(void* ws, size_t ws_bytes, int batch, long long max_samples, Workspace* w) {
+  const size_t need = stats_table_bytes(batch) + octave_bytes(batch, max_samples);
+  if (!ws || ws_bytes < need)
+    return fail(AST_ERR_WORKSPACE, "workspace of %zu bytes is too small, need %zu (ast_workspace_bytes)", ws_bytes, need);
+  if (reinterpret_cast<uintptr_t>(ws) & 255) return fail(AST_ERR_INVALID_ARG, "workspace must be 256-byte aligned");
+  char* p = static_cast<char*>(ws);
+  w->stats_table = reinterpret_cast<float2*>(p);
+  w->octaves = reinterpret_cast<float*>(p + stats_table_bytes(batch));
+  w->used = need;
+  return AST_OK;
+}
+
+static int check_wave(const ast_plan* plan, const float* wave, int batch, long long max_samples, long long wave_stride) {
+  if (!plan) return fail(AST_ERR_INVALID_ARG, "plan is null");
+  if (batch < 0) return fail(AST_ERR_INVALID_ARG, "negative batch");
+  if (batch > 65535) return fail(AST_ERR_INVALID_ARG, "batch %d exceeds 65535 clips per call", batch);
+  if (batch > 0 && !wave) return fail(AST_ERR_INVALID_ARG, "wave is null");
+  if (wave_stride < max_samples) return fail(AST_ERR_INVALID_ARG, "wave_stride %lld < max_samples %lld", wave_stride, max_samples);
+  // torch.stft(center=True, pad_mode="reflect") raises when the pad (512) is not smaller than the input
+  if (max_samples <= kNfft / 2)
+    return fail(AST_ERR_TOO_SHORT, "clips of %lld samples are too short: reflect padding needs more than %d", max_samples,
+                kNfft / 2);
+  return AST_OK;
+}
+
+static OutSpec make_out(const ast_plan* plan, float* out, int layout, int dim1, int f_row, int f_off) {
+  OutSpec o;
+  o.out = out;
+  o.layout = layout;
+  o.dim1 = dim1;
+  o.f_row = f_row;
+  o.f_off = f_off;
+  o.window = plan->cfg.window_size;
+  o.step = plan->cfg.window_size - plan->cfg.overlap_frames;
+  o.stats = nullptr;
+  o.stats_clip_stride = 0;
+  o.f_stats = kFTotal;
+  o.stats_off = 0;
+  return o;
+}
+}  // namespace ast
+
+using namespace ast;
+
+extern "C" {
+
+size_t ast_workspace_bytes(const ast_plan* plan, int32_t batch, int64_t max_samples) {
+  (void)plan;
+  if (batch < 0 || max_samples < 0) return 0;
+  return stats_table_bytes(batch) + octave_bytes(batch, max_samples);
+}
+
+size_t ast_stats_workspace_bytes(const ast_plan* plan, int32_t batch, int64_t max_samples) {
+  if (batch < 0 || max_samples < 0) return 0;
+  const size_t t = (size_t)num_frames(max_samples);
+  return ast_workspace_bytes(plan, batch, max_samples) + align_up(sizeof(float) * 2 * t * kFTotal * (size_t)batch) +
+         align_up(sizeof(double) * 4 * kFTotal * (size_t)batch);
+}
+
+int ast_stft_forward(const ast_plan* plan, const float* wave, const int32_t* lengths, int32_t batch, int64_t max_samples,
+                     int64_t wave_stride, float* out, int32_t t_out, void* stream) {
+  int rc = check_wave(plan, wave, batch, max_samples, wave_stride);
+  if (rc != AST_OK) return rc;
+  if (!out || t_out < 0) return fail(AST_ERR_INVALID_ARG, "ast_stft_forward: bad output");
+  OutSpec o = make_out(plan, out, AST_LAYOUT_FLAT, t_out, kFStft, 0);
+  return launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, (cudaStream_t)stream);
+}
+
+int ast_cqt_forward(const ast_plan* plan, const float* wave, const int32_t* lengths, int32_t batch, int64_t max_samples,
+                    int64_t wave_stride, void* workspace, size_t workspace_bytes, float* out, int32_t t_out, void* stream) {
+  int rc = check_wave(plan, wave, batch, max_samples, wave_stride);
+  if (rc != AST_OK) return rc;
+  if (!out || t_out < 0) return fail(AST_ERR_INVALID_ARG, "ast_cqt_forward: bad output");
+  Workspace w;
+  rc = carve(workspace, workspace_bytes, batch, max_samples, &w);
+  if (rc != AST_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long ws_stride = cqt_ws_clip_stride(max_samples);
+  rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, st);
+  if (rc != AST_OK) return rc;
+  OutSpec o = make_out(plan, out, AST_LAYOUT_FLAT, t_out, kFCqt, 0);  // 84-wide rows, CQT bin 0 at column 0
+  return launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, o, st);
+}
+
+int ast_features_forward(const ast_plan* plan, const float* wave, const int32_t* lengths, int32_t batch,
+                         int64_t max_samples, int64_t wave_stride, const float* mean, const float* std_,
+                         int32_t stats_per_clip, float eps, void* workspace, size_t workspace_bytes, float* out,
+                         int32_t dim1, int32_t layout, int32_t* n_sections, void* stream) {
+  int rc = check_wave(plan, wave, batch, max_samples, wave_stride);
+  if (rc != AST_OK) return rc;
+  if (!out || dim1 < 0) return fail(AST_ERR_INVALID_ARG, "ast_features_forward: bad output");
+  if (layout != AST_LAYOUT_FLAT && layout != AST_LAYOUT_SECTIONS) return fail(AST_ERR_INVALID_ARG, "unknown layout %d", layout);
+  if ((mean == nullptr) != (std_ == nullptr)) return fail(AST_ERR_INVALID_ARG, "mean and std must both be given or both be null");
+  if (layout == AST_LAYOUT_SECTIONS && lengths == nullptr &&
+      num_sections(num_frames(max_samples), plan->cfg.window_size, plan->cfg.overlap_frames) == 0)
+    return fail(AST_ERR_NO_SECTIONS, "%d frames give no section (need >= %d frames)", num_frames(max_samples),
+                (plan->cfg.window_size + 1) / 2);
+  Workspace w;
+  rc = carve(workspace, workspace_bytes, batch, max_samples, &w);
+  if (rc != AST_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float2* table = nullptr;
+  if (mean) {
+    const int n = 2 * kFTotal * (stats_per_clip ? batch : 1);
+    rc = launch_prep_stats(mean, std_, eps, n, w.stats_table, st);
+    if (rc != AST_OK) return rc;
+    table = w.stats_table;
+  }
+  if (n_sections) {
+    rc = launch_count_sections(lengths, batch, max_samples, layout, dim1, plan->cfg.window_size, plan->cfg.overlap_frames,
+                               n_sections, st);
+    if (rc != AST_OK) return rc;
+  }
+  OutSpec o = make_out(plan, out, layout, dim1, kFTotal, 0);
+  o.stats = table;
+  o.stats_clip_stride = stats_per_clip ? 2 * kFTotal : 0;
+  o.stats_off = 0;
+  rc = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st);
+  if (rc != AST_OK) return rc;
+  const long long ws_stride = cqt_ws_clip_stride(max_samples);
+  rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, st);
+  if (rc != AST_OK) return rc;
+  o.f_off = kFStft;
+  o.stats_off = kFStft;
+  return launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, o, st);
+}
+
+int ast_istft_forward(const ast_plan* plan, const float* spec, int32_t batch, int32_t dim1, int32_t f_in, int32_t layout,
+                      int32_t overlap_frames, int32_t original_size, float* wave_out, int64_t out_stride, void* stream) {
+  if (!plan) return fail(AST_ERR_INVALID_ARG, "plan is null");
+  if (batch < 0 || batch > 65535 || dim1 <= 0 || (batch > 0 && (!spec || !wave_out)))
+    return fail(AST_ERR_INVALID_ARG, "ast_istft_forward: bad argument");
+  if (f_in < kFStft) return fail(AST_ERR_SHAPE, "spectrogram rows have %d columns, need at least %d", f_in, kFStft);
+  int n_frames, window = plan->cfg.window_size;
+  if (layout == AST_LAYOUT_FLAT) {
+    n_frames = dim1;
+  } else if (layout == AST_LAYOUT_SECTIONS) {
+    if (overlap_frames < 0 || 2 * overlap_frames > window)
+      return fail(AST_ERR_INVALID_ARG, "need 0 <= 2 * overlap <= window (got %d / %d)", overlap_frames, window);
+    n_frames = (window - overlap_frames) * (dim1 - 1) + window;
+  } else {
+    return fail(AST_ERR_INVALID_ARG, "unknown layout %d", layout);
+  }
+  if (original_size > 0 && original_size < n_frames) n_frames = original_size;
+  if (out_stride < (long long)kHop * (n_frames - 1)) return fail(AST_ERR_INVALID_ARG, "out_stride too small");
+  return launch_istft(plan, spec, batch, dim1, f_in, layout, window, overlap_frames, n_frames, wave_out, out_stride,
+                      (cudaStream_t)stream);
+}
+
+int ast_stats_accumulate_features(const ast_plan* plan, const float* feats, const int32_t* n_frames,
+                                  const int32_t* group_ids, int32_t batch, int32_t t_dim, int32_t f_dim, void* workspace,
+                                  size_t workspace_bytes, int32_t n_groups, double* acc, double* counts, void* stream) {
+  if (!plan || !feats || !acc || !counts || batch < 0 || batch > 65535 || t_dim <= 0 || f_dim <= 0 || n_groups <= 0)
+    return fail(AST_ERR_INVALID_ARG, "ast_stats_accumulate_features: bad argument");
+  const size_t need = sizeof(double) * 4 * (size_t)f_dim * (size_t)batch;
+  if (!workspace || workspace_bytes < need) return fail(AST_ERR_WORKSPACE, "workspace too small: need %zu bytes", need);
+  double* clip_stats = static_cast<double*>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_clip_stats(feats, n_frames, batch, t_dim, f_dim, clip_stats, st);
+  if (rc != AST_OK) return rc;
+  return launch_stats_accumulate(clip_stats, group_ids, batch, f_dim, n_groups, acc, counts, st);
+}
+
+int ast_stats_accumulate(const ast_plan* plan, const float* wave, const int32_t* lengths, const int32_t* group_ids,
+                         int32_t batch, int64_t max_samples, int64_t wave_stride, void* workspace, size_t workspace_bytes,
+                         int32_t n_groups, double* acc, double* counts, void* stream) {
+  int rc = check_wave(plan, wave, batch, max_samples, wave_stride);
+  if (rc != AST_OK) return rc;
+  if (!acc || !counts || n_groups <= 0) return fail(AST_ERR_INVALID_ARG, "ast_stats_accumulate: bad argument");
+  const size_t need = ast_stats_workspace_bytes(plan, batch, max_samples);
+  if (!workspace || workspace_bytes < need) return fail(AST_ERR_WORKSPACE, "workspace too small: need %zu bytes", need);
+  const int t_dim = num_frames(max_samples);
+  const size_t base = ast_workspace_bytes(plan, batch, max_samples);
+  char* p = static_cast<char*>(workspace);
+  float* feats = reinterpret_cast<float*>(p + base);
+  double* clip_stats = reinterpret_cast<double*>(p + base + align_up(sizeof(float) * 2 * (size_t)t_dim * kFTotal * (size_t)batch));
+  int32_t* n_frames = nullptr;
+  // raw (un-normalised) flat features, exactly what compute_stats reduces (compute_separated_stats.py:22-28)
+  rc = ast_features_forward(plan, wave, lengths, batch, max_samples, wave_stride, nullptr, nullptr, 0, 0.f, workspace, base,
+                            feats, t_dim, AST_LAYOUT_FLAT, nullptr, stream);
+  if (rc != AST_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (lengths) {
+    // frame counts per clip, kept in the (now free) normalisation-table region of the workspace
+    n_frames = reinterpret_cast<int32_t*>(p);
+    rc = launch_count_sections(lengths, batch, max_samples, AST_LAYOUT_FLAT, t_dim, plan->cfg.window_size,
+                               plan->cfg.overlap_frames, n_frames, st);
+    if (rc != AST_OK) return rc;
+  }
+  rc = launch_clip_stats(feats, n_frames, batch, t_dim, kFTotal, clip_stats, st);
+  if (rc != AST_OK) return rc;
+  return launch_stats_accumulate(clip_stats, group_ids, batch, kFTotal, n_groups, acc, counts, st);
+}
+
+int ast_profile_enable(int32_t on) {
+  for (auto& r : g_profile) {
+    cudaEventDestroy(r.begin);
+    cudaEventDestroy(r.end);
+  }
+  g_profile.clear();
+  g_profile_on = on != 0;
+  return AST_OK;
+}
+
+int ast_profile_collect(char* names, float* total_ms, int32_t* launches, int32_t capacity, int32_t* n_kernels) {
+  if (!names || !total_ms || !launches || !n_kernels || capacity <= 0)
+    return fail(AST_ERR_INVALID_ARG, "ast_profile_collect: bad argument");
+  std::vector<std::string> keys;
+  for (auto& r : g_profile) {
+    AST_CUDA_TRY(cudaEventSynchronize(r.end));
+    float ms = 0.f;
+    AST_CUDA_TRY(cudaEventElapsedTime(&ms, r.begin, r.end));
+    size_t k = 0;
+    for (; k < keys.size(); ++k)
+      if (keys[k] == r.name) break;
+    if (k == keys.size()) {
+      if ((int)k >= capacity) continue;
+      keys.push_back(r.name);
+      total_ms[k] = 0.f;
+      launches[k] = 0;
+      std::strncpy(names + 32 * k, r.name, 31);
+      names[32 * k + 31] = 0;
+    }
+    total_ms[k] += ms;
+    launches[k] += 1;
+    cudaEventDestroy(r.begin);
+    cudaEventDestroy(r.end);
+  }
+  g_profile.clear();
+  *n_kernels = (int32_t)keys.size();
+  return AST_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the spectral front-end (BASELINE.json metric: audio-sec/sec STFT+CQT+norm, and iSTFT).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step is one pass of the hot path over one batch of synthetic input: BASELINE.json configs[1],
+64 clips x 10 s (220 500 samples @ 22 050 Hz) per GPU -> STFT + CQT + per-bin normalisation ->
+(64, 4, 2, 287, 597) float32 sections.  N > 1 (launched by torchrun, one rank per GPU) shards clips
+over ranks with no data-path collective (weak scaling); timing is CUDA events on the launching stream,
+bracketed by barrier + synchronize, max over ranks.  Rank 0 prints ONE JSON line.
+
+Extra objects on the line: ``roofline`` (dominant kernel, timed live with CUDA events in a second pass
+of the same K steps), ``cpu_baseline`` (oracle port of the reference CPU path on the host cores, rank 0,
+N = 1), ``e2e`` (same metric through the public API from pinned HOST buffers, H2D + D2H inside the timed
+region), ``istft`` (the reconstruction leg of the metric), ``clocks`` (nvidia-smi during the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CLIPS_PER_GPU = 64
+CLIP_SAMPLES = 220500
+SAMPLE_RATE = 22050
+CLIP_SECONDS = CLIP_SAMPLES / SAMPLE_RATE  # 10.0
+ISTFT_SECONDS = 219904 / SAMPLE_RATE       # audio reconstructed per clip by the iSTFT leg (860 frames)
+METRIC = "audio-sec/sec STFT+CQT+norm"
+UNIT = "audio-s/s"
+# algorithmic bytes per clip (SURVEY.md §8d / DESIGN.md §5)
+BYTES_WAVE = CLIP_SAMPLES * 4
+BYTES_SECTIONS_STFT = 4 * 2 * 287 * 513 * 4
+BYTES_SECTIONS_CQT = 4 * 2 * 287 * 84 * 4
+BYTES_FEATURE_PATH = BYTES_WAVE + 4 * 2 * 287 * 597 * 4          # 6 365 008
+BYTES_ISTFT_PATH = BYTES_SECTIONS_STFT + 219904 * 4               # 5 591 008
+_OCT = [220500, 110250, 55125, 27563, 13782, 6891, 3446]
+KERNEL_BYTES_PER_CLIP = {  # compulsory input + output bytes of each kernel as the path is split today
+    "stft_kernel": BYTES_WAVE + BYTES_SECTIONS_STFT,
+    "decimate2_kernel": (sum(_OCT[:6]) + sum(_OCT[1:])) * 4 / 6.0,  # average of the six launches
+    "cqt_kernel": sum(_OCT) * 4 + BYTES_SECTIONS_CQT,
+    "istft_kernel": BYTES_ISTFT_PATH,
+}
+STATS_NPZ = os.path.join(ROOT, "tests", "golden", "train_set_stats", "stats_stft_cqt_piano.npz")
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "configs[1]: 64 synthetic 10 s clips per GPU -> STFT+CQT+normalise -> (64,4,2,287,597) f32 sections",
+        "clips_per_gpu": CLIPS_PER_GPU, "clip_samples": CLIP_SAMPLES, "sample_rate": SAMPLE_RATE,
+        "n_fft": 1024, "hop": 256, "cqt_bins": 84, "window": 287, "overlap": 96,
+        "stats": "train_set_stats/stats_stft_cqt_piano.npz",
+        "parallelism": f"clips sharded over {n_gpus} rank(s), no data-path collective",
+        "l2_policy": "working set per step (56 MB in + 351 MB out) exceeds the 126 MB L2; no explicit flush",
+    }
+
+
+def make_clips(n_distinct=8):
+    """(64, 220500) float32: n_distinct synthetic clips (piano / violin alternating), tiled with fixed gains."""
+    import numpy as np
+
+    synth = importlib.import_module("audio_style_transfer_b200.synth")
+    base = synth.batch(n_distinct)
+    reps = CLIPS_PER_GPU // n_distinct
+    gains = np.random.default_rng(0).uniform(0.7, 1.3, CLIPS_PER_GPU).astype(np.float32)
+    return np.tile(base, (reps, 1)) * gains[:, None]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    FIELDS = ["clocks.sm", "clocks.max.sm", "power.draw", "clocks_event_reasons.hw_slowdown",
+              "clocks_event_reasons.hw_thermal_slowdown", "clocks_event_reasons.sw_thermal_slowdown",
+              "clocks_event_reasons.sw_power_cap"]
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc, self.thread = index, [], None, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={','.join(self.FIELDS)}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) != len(self.FIELDS):
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:]):
+                if val.lower() == "active":
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's CPU path (oracle port: torch.stft + restated librosa CQT + eager normalise / section
+    loops) on the host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+
+    from oracle import cpu_baseline as cb
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_clips = 4
+    wave = torch.from_numpy(make_clips(4)[:sample_clips].copy())
+    z = np.load(STATS_NPZ)
+    mean = torch.from_numpy(np.concatenate([z["stft_mean"], z["cqt_mean"]], axis=1))
+    std = torch.from_numpy(np.concatenate([z["stft_std"], z["cqt_std"]], axis=1))
+    for _ in range(args.warmup):
+        cb.features_batch(wave, mean, std)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = cb.features_batch(wave, mean, std)
+    dt = time.perf_counter() - t0
+    assert tuple(out.shape) == (sample_clips, 4, 2, 287, 597)
+    value = sample_clips * CLIP_SECONDS * args.steps / dt
+    sample = f"{sample_clips} of the 64 clips per step (per-clip loop, as the reference DataLoader with num_workers=0)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "torch.stft / eager torch ops exactly as utilityFunctions.py + dataloader.py call them; the CQT is the "
+                "NumPy/SciPy restatement of librosa.cqt (librosa is not installable here)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(wave_np, mean, std):
+    import torch
+
+    from oracle import cpu_baseline as cb
+
+    cores = os.cpu_count() or 1
+    prev = torch.get_num_threads()
+    torch.set_num_threads(cores)
+    n = 32
+    wave = torch.from_numpy(wave_np[:n].copy())
+    cb.features_batch(wave[:1], mean, std)  # warm-up (FFT plans, filter tables)
+    t0 = time.perf_counter()
+    cb.features_batch(wave, mean, std)
+    dt = time.perf_counter() - t0
+    spec = torch.randn(8, 4, 2, 287, 513)
+    cb.istft_batch(spec[:1])
+    t1 = time.perf_counter()
+    cb.istft_batch(spec)
+    dt_i = time.perf_counter() - t1
+    torch.set_num_threads(prev)
+    return {
+        "value": n * CLIP_SECONDS / dt, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"{n} of the 64 clips, one pass, per-clip loop (torch.stft + restated librosa CQT + eager normalise/sections)",
+        "istft_value": 8 * ISTFT_SECONDS / dt_i, "istft_sample": "8 clips merge + torch.istft",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (used under ncu)")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    frontend = importlib.import_module("audio_style_transfer_b200.frontend")
+    dl = importlib.import_module("audio_style_transfer_b200.dataloader")
+    lib = importlib.import_module("audio_style_transfer_b200._lib")
+    fe = frontend.FrontEnd(device)
+    mean, std = dl.load_stats_npz(STATS_NPZ)
+    mean_d, std_d = mean.to(device), std.to(device)
+
+    wave_np = make_clips()
+    wave = torch.from_numpy(wave_np).to(device)
+    out = torch.empty((CLIPS_PER_GPU, 4, 2, 287, 597), dtype=torch.float32, device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        barrier()
+        return ms
+
+    def step():
+        fe.features(wave, mean=mean_d, std=std_d, layout="sections", out=out)
+
+    with ClockSampler(local_rank) as clocks:
+        ms_total = timed(step, args.steps, args.warmup)
+    ms_step = ms_total / args.steps
+    value = world * CLIPS_PER_GPU * CLIP_SECONDS / (ms_step / 1e3)
+
+    # ---- iSTFT leg: decoder-shaped (64, 4, 2, 287, 513) -> merge(overlap 96) -> iSTFT -> (64, 219904)
+    spec = out[..., :513].contiguous()
+
+    def istft_step():
+        fe.istft(spec, layout="sections", overlap=96, original_size=862)
+
+    ms_istft = timed(istft_step, args.steps, args.warmup) / args.steps
+    istft_value = world * CLIPS_PER_GPU * ISTFT_SECONDS / (ms_istft / 1e3)
+
+    # ---- roofline pass: the same K steps with per-kernel CUDA events (ast_profile_*), rank-local
+    lib.profile_enable(True)
+    for _ in range(args.steps):
+        step()
+        istft_step()
+    torch.cuda.synchronize()
+    prof = lib.profile_collect()
+    lib.profile_enable(False)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+    kernels = {}
+    feature_ms = 0.0
+    for name, (tot, n) in prof.items():
+        avg = tot / max(n, 1)
+        nbytes = KERNEL_BYTES_PER_CLIP.get(name, 0) * CLIPS_PER_GPU
+        kernels[name] = {"avg_ms": avg, "launches_per_step": n / args.steps, "ms_per_step": tot / args.steps,
+                         "achieved_gbs": nbytes / (avg * 1e-3) / 1e9 if avg > 0 else None}
+        if name != "istft_kernel":
+            feature_ms += tot / args.steps
+    feat_kernels = {k: v for k, v in kernels.items() if k != "istft_kernel"}
+    dom = max(feat_kernels, key=lambda k: feat_kernels[k]["ms_per_step"]) if feat_kernels else None
+    roofline = None
+    if dom:
+        a = kernels[dom]["achieved_gbs"]
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
+                    "traffic": None, "peak_source": peak_src,
+                    "share_of_step": kernels[dom]["ms_per_step"] / feature_ms if feature_ms else None,
+                    "path": {"bytes_per_clip": BYTES_FEATURE_PATH,
+                             "achieved": BYTES_FEATURE_PATH * CLIPS_PER_GPU / (ms_step * 1e-3) / 1e9,
+                             "frac": BYTES_FEATURE_PATH * CLIPS_PER_GPU / (ms_step * 1e-3) / 1e9 / peak},
+                    "istft": {"bytes_per_clip": BYTES_ISTFT_PATH,
+                              "achieved": BYTES_ISTFT_PATH * CLIPS_PER_GPU / (ms_istft * 1e-3) / 1e9,
+                              "frac": BYTES_ISTFT_PATH * CLIPS_PER_GPU / (ms_istft * 1e-3) / 1e9 / peak},
+                    "kernels": kernels}
+
+    # ---- end to end through the public API with HOST buffers (pinned): H2D + kernels + D2H per step
+    e2e = None
+    if not args.no_e2e:
+        host_in = torch.from_numpy(wave_np).pin_memory()
+        host_out = torch.empty(out.shape, dtype=torch.float32).pin_memory()
+        dev_in = torch.empty_like(wave)
+
+        def e2e_step():
+            dev_in.copy_(host_in, non_blocking=True)
+            fe.features(dev_in, mean=mean_d, std=std_d, layout="sections", out=out)
+            host_out.copy_(out, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_steps = max(3, min(args.steps, 10))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        e2e = {"value": world * CLIPS_PER_GPU * CLIP_SECONDS * e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(host_in.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4),
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+               "how": "pinned host waveforms -> cudaMemcpyAsync -> ast_features_forward -> cudaMemcpyAsync to pinned host "
+                      "(full 351 MB feature tensor) -> synchronize, every step"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_leg(wave_np, mean, std)
+
+    if rank == 0:
+        launches_per_step = 1 + 1 + 1 + 6 + 1  # prep_stats, count_sections, stft, 6 x decimate2, cqt
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps, "clocks": clocks.summary(),
+            "istft": {"metric": "audio-sec/sec iSTFT (merge + inverse STFT)", "value": istft_value, "unit": UNIT,
+                      "ms_per_step": ms_istft, "gpu_launches": args.steps,
+                      "workload": "configs[4] at B=64 per GPU: (64,4,2,287,513) -> (64,219904)"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
