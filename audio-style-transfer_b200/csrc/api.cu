@@ -179,7 +179,7 @@ int ast_features_forward(const ast_plan* plan, const float* wave, const int32_t*
 int ast_istft_forward(const ast_plan* plan, const float* spec, int32_t batch, int32_t dim1, int32_t f_in, int32_t layout,
                       int32_t overlap_frames, int32_t original_size, float* wave_out, int64_t out_stride, void* stream) {
   if (!plan) return fail(AST_ERR_INVALID_ARG, "plan is null");
-  if (batch < 0 || batch > 65535 || dim1 <= 0 || (batch > 0 && (!spec || !wave_out)))
+  if (batch < 0 || batch > 65535 || dim1 <= 0 || (batch > 0 && !spec))
     return fail(AST_ERR_INVALID_ARG, "ast_istft_forward: bad argument");
   if (f_in < kFStft) return fail(AST_ERR_SHAPE, "spectrogram rows have %d columns, need at least %d", f_in, kFStft);
   int n_frames, window = plan->cfg.window_size;
@@ -194,6 +194,7 @@ int ast_istft_forward(const ast_plan* plan, const float* spec, int32_t batch, in
   }
   if (original_size > 0 && original_size < n_frames) n_frames = original_size;
   if (out_stride < (long long)kHop * (n_frames - 1)) return fail(AST_ERR_INVALID_ARG, "out_stride too small");
+  if (batch > 0 && n_frames > 1 && !wave_out) return fail(AST_ERR_INVALID_ARG, "wave_out is null");
   return launch_istft(plan, spec, batch, dim1, f_in, layout, window, overlap_frames, n_frames, wave_out, out_stride,
                       (cudaStream_t)stream);
 }
