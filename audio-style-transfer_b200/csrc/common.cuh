@@ -132,7 +132,8 @@ __device__ __forceinline__ RowDest row_dest(const OutSpec& o, int b, int t, int 
 struct ast_plan {
   ast_config cfg;
   int sm_count;
-  float2* d_tw;         // 1024 forward twiddles exp(-2 pi i m / 1024)
+  float2* d_tw1;        // stage-1 twiddles [16][16]  (fft_core.h)
+  float2* d_tw2;        // stage-2 twiddles [16][64]
   float* d_hann;        // 1024 periodic Hann
   float* d_hann_inv_n;  // Hann / 1024 (iSTFT synthesis window with the irfft scale folded in)
   float* d_hann_sq;     // Hann^2 (iSTFT envelope)

@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(kCqtThreads) cqt_kernel(const CqtParams p) {
   const float2* st0 = nullptr;
   if (p.out.stats) st0 = p.out.stats + (long long)b * p.out.stats_clip_stride + p.out.stats_off;
 
-  for (int oct = 0; oct < kOctaves; ++oct) {
+  {
+    const int oct = blockIdx.z;  // one octave per CTA: 7x more CTAs to fill the machine
     float acc[kCqtCols];
 #pragma unroll
     for (int c = 0; c < kCqtCols; ++c) acc[c] = 0.f;
@@ -129,7 +130,7 @@ int launch_cqt(const ast_plan* plan, const float* wave, const int32_t* lengths, 
   p.vec_ok = (wave_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(wave) & 15) == 0);
   p.out = out;
   if (p.slots == 0 || batch == 0) return AST_OK;
-  dim3 grid((unsigned)((p.slots + kCqtThreads - 1) / kCqtThreads), (unsigned)batch);
+  dim3 grid((unsigned)((p.slots + kCqtThreads - 1) / kCqtThreads), (unsigned)batch, kOctaves);
   ProfileSpan span("cqt_kernel", st);
   cqt_kernel<<<grid, kCqtThreads, 0, st>>>(p);
   AST_LAUNCH_CHECK("cqt_kernel");

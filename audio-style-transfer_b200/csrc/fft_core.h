@@ -85,27 +85,46 @@ AST_HD void fft16(float2 (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = t[i];
 }
 
-// stage 1: thread tid holds v[n1] = z[64 n1 + tid].  tw[m] = exp(-2 pi i m / 1024).
-AST_HD void fft1024_stage1(float2 (&v)[16], int tid, const float2* tw, float2* buf1) {
+// Twiddle tables (built on the host in double precision):
+//   t1[k1 * 16 + n2]  = exp(-2 pi i n2 k1 / 256)                 (stage 1; a warp reads one k1 row -> no bank conflicts)
+//   t2[k2 * 64 + tid] = exp(-2 pi i n3 (k1 + 16 k2) / 1024), tid = k1 + 16 n3   (stage 2; lane-contiguous)
+constexpr int kTw1Size = 16 * 16;
+constexpr int kTw2Size = 16 * 64;
+
+inline void fill_twiddle_tables(float2* t1, float2* t2) {
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int k1 = 0; k1 < 16; ++k1)
+    for (int n2 = 0; n2 < 16; ++n2) {
+      const double a = -two_pi * (double)(n2 * k1) / 256.0;
+      t1[k1 * 16 + n2] = make_float2((float)cos(a), (float)sin(a));
+    }
+  for (int k2 = 0; k2 < 16; ++k2)
+    for (int tid = 0; tid < 64; ++tid) {
+      const int k1 = tid & 15, n3 = tid >> 4;
+      const double a = -two_pi * (double)(n3 * (k1 + 16 * k2)) / 1024.0;
+      t2[k2 * 64 + tid] = make_float2((float)cos(a), (float)sin(a));
+    }
+}
+
+// stage 1: thread tid holds v[n1] = z[64 n1 + tid]
+AST_HD void fft1024_stage1(float2 (&v)[16], int tid, const float2* t1, float2* buf1) {
   fft16(v);
   const int n2 = tid >> 2;
   buf1[tid] = v[0];
 #pragma unroll
-  for (int k1 = 1; k1 < 16; ++k1) buf1[k1 * kBuf1Stride + tid] = cmul(v[k1], tw[4 * n2 * k1]);
+  for (int k1 = 1; k1 < 16; ++k1) buf1[k1 * kBuf1Stride + tid] = cmul(v[k1], t1[k1 * 16 + n2]);
 }
 
 // stage 2: thread tid = k1 + 16 n3 gathers over n2, transforms, twiddles, scatters to buf2[n3][q]
-AST_HD void fft1024_stage2(int tid, const float2* tw, const float2* buf1, float2* buf2) {
+AST_HD void fft1024_stage2(int tid, const float2* t2, const float2* buf1, float2* buf2) {
   const int k1 = tid & 15, n3 = tid >> 4;
   float2 v[16];
 #pragma unroll
   for (int n2 = 0; n2 < 16; ++n2) v[n2] = buf1[k1 * kBuf1Stride + 4 * n2 + n3];
   fft16(v);
+  // unconditional multiply (t2 = 1 exactly where n3 == 0) keeps the warp convergent
 #pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) {
-    const int q = k1 + 16 * k2;
-    buf2[n3 * 256 + q] = (n3 == 0) ? v[k2] : cmul(v[k2], tw[n3 * q]);
-  }
+  for (int k2 = 0; k2 < 16; ++k2) buf2[n3 * 256 + k1 + 16 * k2] = cmul(v[k2], t2[k2 * 64 + tid]);
 }
 
 // stage 3 helper: the four outputs Z[q + 256 a], a = 0..3
@@ -119,45 +138,50 @@ AST_HD void fft1024_stage3_column(int q, const float2* buf2, float2 (&z)[4]) {
 
 // Hermitian separation of one conjugate pair: zk = Z[k], zp = Z[(N - k) mod N], k <= 512.
 //   frame A bin k = (zk + conj(zp)) / 2          frame B bin k = (zk - conj(zp)) / (2 i)
-template <class Emit>
+// With kHalve == false the four values are emitted WITHOUT the factor 1/2 (the caller folds it
+// into its own scaling, e.g. the normalisation multiply).
+template <bool kHalve, class Emit>
 AST_HD void separate_pair(int k, float2 zk, float2 zp, Emit& emit) {
-  emit(k, 0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y), 0.5f * (zk.y + zp.y), 0.5f * (zp.x - zk.x));
+  if (kHalve)
+    emit(k, 0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y), 0.5f * (zk.y + zp.y), 0.5f * (zp.x - zk.x));
+  else
+    emit(k, zk.x + zp.x, zk.y - zp.y, zk.y + zp.y, zp.x - zk.x);
 }
 
 // stage 3 of the forward transform of two real frames: emits all 513 bins of both frames.
 // emit(k, a_re, a_im, b_re, b_im).  Thread j emits 8 bins (thread 0: 9).
-template <class Emit>
+template <bool kHalve, class Emit>
 AST_HD void fft1024_stage3_real_pair(int j, const float2* buf2, Emit& emit) {
   float2 za[4], zb[4];
   if (j != 0) {
     // columns q = j and 256 - j hold bins k = j + 256 a  <->  N - k = (256 - j) + 256 (3 - a)
     fft1024_stage3_column(j, buf2, za);
     fft1024_stage3_column(256 - j, buf2, zb);
-    separate_pair(j, za[0], zb[3], emit);
-    separate_pair(256 + j, za[1], zb[2], emit);
-    separate_pair(512 - j, zb[1], za[2], emit);
-    separate_pair(256 - j, zb[0], za[3], emit);
+    separate_pair<kHalve>(j, za[0], zb[3], emit);
+    separate_pair<kHalve>(256 + j, za[1], zb[2], emit);
+    separate_pair<kHalve>(512 - j, zb[1], za[2], emit);
+    separate_pair<kHalve>(256 - j, zb[0], za[3], emit);
     // columns q = 128 - j and 128 + j: k = 128 - j + 256 a  <->  N - k = (128 + j) + 256 (3 - a)
     fft1024_stage3_column(128 - j, buf2, za);
     fft1024_stage3_column(128 + j, buf2, zb);
-    separate_pair(128 - j, za[0], zb[3], emit);
-    separate_pair(384 - j, za[1], zb[2], emit);
-    separate_pair(384 + j, zb[1], za[2], emit);
-    separate_pair(128 + j, zb[0], za[3], emit);
+    separate_pair<kHalve>(128 - j, za[0], zb[3], emit);
+    separate_pair<kHalve>(384 - j, za[1], zb[2], emit);
+    separate_pair<kHalve>(384 + j, zb[1], za[2], emit);
+    separate_pair<kHalve>(128 + j, zb[0], za[3], emit);
   } else {
     fft1024_stage3_column(0, buf2, za);  // Z[0], Z[256], Z[512], Z[768]
-    separate_pair(0, za[0], za[0], emit);
-    separate_pair(256, za[1], za[3], emit);
-    separate_pair(512, za[2], za[2], emit);
+    separate_pair<kHalve>(0, za[0], za[0], emit);
+    separate_pair<kHalve>(256, za[1], za[3], emit);
+    separate_pair<kHalve>(512, za[2], za[2], emit);
     fft1024_stage3_column(128, buf2, za);  // Z[128], Z[384], Z[640], Z[896]
-    separate_pair(128, za[0], za[3], emit);
-    separate_pair(384, za[1], za[2], emit);
+    separate_pair<kHalve>(128, za[0], za[3], emit);
+    separate_pair<kHalve>(384, za[1], za[2], emit);
     fft1024_stage3_column(64, buf2, za);   // Z[64], Z[320], Z[576], Z[832]
     fft1024_stage3_column(192, buf2, zb);  // Z[192], Z[448], Z[704], Z[960]
-    separate_pair(64, za[0], zb[3], emit);
-    separate_pair(320, za[1], zb[2], emit);
-    separate_pair(448, zb[1], za[2], emit);
-    separate_pair(192, zb[0], za[3], emit);
+    separate_pair<kHalve>(64, za[0], zb[3], emit);
+    separate_pair<kHalve>(320, za[1], zb[2], emit);
+    separate_pair<kHalve>(448, zb[1], za[2], emit);
+    separate_pair<kHalve>(192, zb[0], za[3], emit);
   }
 }
 
@@ -179,6 +203,23 @@ AST_HD void fft1024_stage3_complex(int j, const float2* buf2, Emit& emit) {
   }
 }
 
+// stage 3 of a plain complex transform, column-wise: emit.template col<s>(q, z) with z[a] = Z[q + 256 a],
+// s = 0..3 the (compile-time) slot of column q in thread j's set, so per-column state can live in registers.
+template <class Emit>
+AST_HD void fft1024_stage3_columns(int j, const float2* buf2, Emit& emit) {
+  float2 z[4];
+  const bool first = j == 0;
+  const int q0 = first ? 0 : j, q1 = first ? 128 : 256 - j, q2 = first ? 64 : 128 - j, q3 = first ? 192 : 128 + j;
+  fft1024_stage3_column(q0, buf2, z);
+  emit.template col<0>(q0, z);
+  fft1024_stage3_column(q1, buf2, z);
+  emit.template col<1>(q1, z);
+  fft1024_stage3_column(q2, buf2, z);
+  emit.template col<2>(q2, z);
+  fft1024_stage3_column(q3, buf2, z);
+  emit.template col<3>(q3, z);
+}
+
 // Packs two Hermitian half-spectra (513 bins each, imag of bins 0 / 512 ignored as torch.istft
 // does) into conj(Z)[m], Z = XA + i XB extended to 1024 bins, so that
 //   forward_fft(conj Z)[n] = N * conj(a[n] + i b[n])   ->  a[n] = Re / N,  b[n] = -Im / N.
@@ -186,6 +227,23 @@ AST_HD void fft1024_stage3_complex(int j, const float2* buf2, Emit& emit) {
 AST_HD float2 pack_conj_hermitian_pair(int m, float2 xa, float2 xb) {
   if (m == 0 || m == 512) return make_float2(xa.x, -xb.x);
   if (m < 512) return make_float2(xa.x - xb.y, -(xa.y + xb.x));
+  return make_float2(xa.x + xb.y, -(xb.x - xa.y));
+}
+
+// The same packing for stage-1 register n1 of thread tid (m = 64 n1 + tid), with the case analysis
+// resolved at compile time: bin index kk = 64 n1 + tid (n1 < 8) or 64 (16 - n1) - tid (n1 >= 8), and
+// only (n1 in {0, 8}, tid == 0) are the self-conjugate bins 0 / 512.
+template <int N1>
+AST_HD int ihalf_bin(int tid) {
+  return N1 < 8 ? 64 * N1 + tid : 64 * (16 - N1) - tid;
+}
+template <int N1>
+AST_HD float2 ihalf_pack(int tid, float2 xa, float2 xb) {
+  if ((N1 == 0 || N1 == 8) && tid == 0) {
+    xa.y = 0.f;
+    xb.y = 0.f;
+  }
+  if (N1 < 8) return make_float2(xa.x - xb.y, -(xa.y + xb.x));
   return make_float2(xa.x + xb.y, -(xb.x - xa.y));
 }
 

@@ -1,4 +1,4 @@
-// istft.cu - K5: section merge + C2R inverse FFT-1024 + Hann synthesis window + gather overlap-add
+// istft.cu - K5: section merge + C2R inverse FFT-1024 + Hann synthesis window + overlap-add
 // + envelope normalisation + centre trim, in one kernel.  Replaces sections2spectrogram
 // (utilityFunctions.py:265-283) and torch.istft as called by inverse_STFT (utilityFunctions.py:62-82;
 // the device-aware copy in style_transfer_inference_test.ipynb cell 1) and by
@@ -7,135 +7,198 @@
 // torch.istft semantics: x_t = irfft(X[:, t], n = 1024) (1/N scale, imaginary parts of bins 0 and
 // 512 ignored); output sample n in [0, 256 (T - 1)) sits at p = n + 512 of the untrimmed signal and is
 //     y[n] = sum_t w[p - 256 t] x_t[p - 256 t] / sum_t w[p - 256 t]^2,
-// t over the (at most 4) frames with 0 <= p - 256 t < 1024.  The sum is a GATHER over frames kept in
-// shared memory: no atomics, deterministic.
+// t over the (at most 4) frames with 0 <= p - 256 t < 1024.
 //
-// A CTA owns 13 consecutive 256-sample output segments of one clip and therefore needs 16 frames
-// (one before, two after).  Two frames share one complex FFT (see fft_core.h).  Shared memory:
-// 8 KB twiddles + 4 x 16.1 KB exchange + 64 KB windowed frames = 138 KB.
+// Formulation: a 64-thread CTA walks a RUN of consecutive frames of one clip, two frames per complex
+// FFT.  After stage 3 thread j holds, for each of its four columns q, the samples q + 256 a (a = 0..3)
+// of both frames - i.e. the same offset q of four consecutive 256-sample output segments.  Every
+// contribution to output position (segment g, offset q) is therefore produced by the SAME thread, so the
+// overlap-add runs in registers: no atomics, no shared-memory frame store, deterministic order
+// (frames ascending, like torch's fold).  A run of R segments needs 4 halo frames.
+// Shared memory per CTA: 10 KB twiddle tables + 16.1 KB exchange buffers.
 #include "common.cuh"
 
 namespace ast {
 
-constexpr int kIstftGroups = 4;
-constexpr int kIstftThreads = kIstftGroups * kFftThreads;
-constexpr int kIstftFrames = 16;
-constexpr int kIstftSegs = 13;
-constexpr size_t kIstftSmem =
-    sizeof(float2) * (kFftN + kIstftGroups * (kBuf1Size + kBuf2Size)) + sizeof(float) * kIstftFrames * kFftN;
+constexpr int kIstftThreads = kFftThreads;  // 64
+constexpr size_t kIstftSmem = sizeof(float2) * (kTw1Size + kTw2Size + kBuf1Size + kBuf2Size);
 
 struct IstftParams {
   const float* spec;
-  int batch, dim1, f_in, layout;
+  int dim1, f_in, layout;
   int window, sec_hop;   // SECTIONS: rows per section, frames between section starts
   int n_frames;          // T' after merge / crop
+  int run_segs;          // R: output segments per CTA (even)
   long long clip_stride; // floats per clip of spec
+  long long plane;       // floats between the real and the imaginary plane of a row
   float* out;
   long long out_stride;
-  const float2* tw;
+  const float2* t1;
+  const float2* t2;
   const float* hann_inv_n;
-  const float* hann_sq;
 };
 
-// complex bin kk of merged frame t (count-normalised average of the sections covering it)
-__device__ __forceinline__ float2 load_bin(const IstftParams& p, const float* __restrict__ clip, int t, int kk) {
+// Row pointers (real plane) of merged frame t: one row, or two section rows to be averaged
+// (count-normalised overlap average of sections2spectrogram, utilityFunctions.py:276-282).
+struct FrameRows {
+  const float* r0;
+  const float* r1;  // nullptr when a single row covers the frame
+};
+
+__device__ __forceinline__ FrameRows merged_rows(const IstftParams& p, const float* __restrict__ clip, int t) {
+  FrameRows f;
+  f.r1 = nullptr;
   if (p.layout == AST_LAYOUT_FLAT) {
-    const float* r = clip + (long long)t * p.f_in + kk;
-    return make_float2(__ldg(r), __ldg(r + (long long)p.dim1 * p.f_in));
+    f.r0 = clip + (long long)t * p.f_in;
+    return f;
   }
-  const long long plane = (long long)p.window * p.f_in;
   int s_hi = t / p.sec_hop;
   if (s_hi > p.dim1 - 1) s_hi = p.dim1 - 1;
-  float re = 0.f, im = 0.f, cnt = 0.f;
-  for (int s = s_hi; s >= 0 && s >= s_hi - 1; --s) {
-    const int tau = t - s * p.sec_hop;
-    if (tau >= p.window) break;
-    const float* r = clip + ((long long)s * 2 * p.window + tau) * p.f_in + kk;
-    re += __ldg(r);
-    im += __ldg(r + plane);
-    cnt += 1.f;
-  }
-  cnt = fmaxf(cnt, 1.f);  // count.clamp(min=1.0), utilityFunctions.py:282
-  return make_float2(re / cnt, im / cnt);
+  const int tau = t - s_hi * p.sec_hop;
+  f.r0 = clip + ((long long)s_hi * 2 * p.window + tau) * p.f_in;
+  if (s_hi >= 1 && tau + p.sec_hop < p.window)
+    f.r1 = clip + ((long long)(s_hi - 1) * 2 * p.window + tau + p.sec_hop) * p.f_in;
+  return f;
 }
 
-struct IstftEmit {
-  float* fa;  // windowed frame A in shared memory (1024 floats)
-  float* fb;
-  const float* w;
-  __device__ __forceinline__ void operator()(int n, float2 z) const {
-    const float wn = __ldg(w + n);
-    fa[n] = z.x * wn;
-    fb[n] = -z.y * wn;
+__device__ __forceinline__ float2 load_bin(const FrameRows& f, long long plane, int kk, bool live) {
+  if (!live) return make_float2(0.f, 0.f);
+  float re = __ldg(f.r0 + kk), im = __ldg(f.r0 + plane + kk);
+  if (f.r1) {
+    // ascending section order like the reference's += loop, then / count (= 2)
+    re = (__ldg(f.r1 + kk) + re) * 0.5f;
+    im = (__ldg(f.r1 + plane + kk) + im) * 0.5f;
+  }
+  return make_float2(re, im);
+}
+
+template <int N1>
+__device__ __forceinline__ void load_inputs(float2 (&v)[16], int tid, const FrameRows& fa, const FrameRows& fb,
+                                            long long plane, bool live_a, bool live_b) {
+  const int kk = ihalf_bin<N1>(tid);
+  v[N1] = ihalf_pack<N1>(tid, load_bin(fa, plane, kk, live_a), load_bin(fb, plane, kk, live_b));
+  if constexpr (N1 < 15) load_inputs<N1 + 1>(v, tid, fa, fb, plane, live_a, live_b);
+}
+
+// Register-resident overlap-add state of one thread: for each of its 4 columns, partial sums of the
+// five segments t .. t+4 touched by the frame pair (t, t+1).
+struct OlaEmit {
+  float acc[4][5];
+  float wn[4][4];   // hann[q + 256 a] / 1024
+  template <int S>
+  __device__ __forceinline__ void col(int /*q*/, const float2 (&z)[4]) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      acc[S][a] = fmaf(z[a].x, wn[S][a], acc[S][a]);           // frame A (real lane)  -> segment t + a
+      acc[S][a + 1] = fmaf(-z[a].y, wn[S][a], acc[S][a + 1]);  // frame B (-imag lane) -> segment t + 1 + a
+    }
   }
 };
 
-__global__ void __launch_bounds__(kIstftThreads, 1) istft_kernel(const IstftParams p) {
-  extern __shared__ __align__(16) float2 smem[];
-  float2* tw = smem;
-  const int group = threadIdx.x >> 6, tid = threadIdx.x & 63;
-  float2* buf1 = smem + kFftN + group * (kBuf1Size + kBuf2Size);
-  float2* buf2 = buf1 + kBuf1Size;
-  float* frames = reinterpret_cast<float*>(smem + kFftN + kIstftGroups * (kBuf1Size + kBuf2Size));
-  for (int i = threadIdx.x; i < kFftN; i += kIstftThreads) tw[i] = p.tw[i];
-
-  const int b = blockIdx.y;
-  const int seg0 = blockIdx.x * kIstftSegs;
-  const int t_first = seg0 - 1;
-  const float* __restrict__ clip = p.spec + (long long)b * p.clip_stride;
-  __syncthreads();
-
-  for (int round = 0; round < kIstftFrames / 2 / kIstftGroups; ++round) {
-    const int pair = round * kIstftGroups + group;
-    const int ta = t_first + 2 * pair, tb = ta + 1;
-    const bool live_a = ta >= 0 && ta < p.n_frames, live_b = tb >= 0 && tb < p.n_frames;
-    float* fa = frames + (2 * pair) * kFftN;
-    float* fb = fa + kFftN;
-    if (live_a || live_b) {
-      float2 v[16];
+// writes segments t and t + 1 (if they belong to this run) from acc[.][0] and acc[.][1]
+__device__ __forceinline__ void emit_segments(const IstftParams& p, const OlaEmit& ola, const float (&wsq)[4][4],
+                                              const float (&renv)[4], const int (&qs)[4], float* __restrict__ y, int t,
+                                              int g0, int g1) {
 #pragma unroll
-      for (int n1 = 0; n1 < 16; ++n1) {
-        const int m = 64 * n1 + tid;
-        const int kk = m <= 512 ? m : kFftN - m;
-        const float2 xa = live_a ? load_bin(p, clip, ta, kk) : make_float2(0.f, 0.f);
-        const float2 xb = live_b ? load_bin(p, clip, tb, kk) : make_float2(0.f, 0.f);
-        v[n1] = pack_conj_hermitian_pair(m, xa, xb);
+  for (int c = 0; c < 2; ++c) {
+    const int g = t + c;
+    if (g >= g0 && g < g1) {
+      float* __restrict__ yo = y + (long long)(g - 2) * kHop;
+      if (g >= 3 && g < p.n_frames) {
+        // interior: all four frames exist, the envelope is a per-column constant
+#pragma unroll
+        for (int s = 0; s < 4; ++s) yo[qs[s]] = ola.acc[s][c] * renv[s];
+      } else {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          // envelope: sum of w^2 over the live frames g - a, a = 3..0 (frame-ascending order)
+          float env = 0.f;
+#pragma unroll
+          for (int a = 3; a >= 0; --a)
+            if (g - a >= 0 && g - a < p.n_frames) env += wsq[s][a];
+          yo[qs[s]] = ola.acc[s][c] / env;
+        }
       }
-      fft1024_stage1(v, tid, tw, buf1);
     }
-    __syncthreads();
-    if (live_a || live_b) fft1024_stage2(tid, tw, buf1, buf2);
-    __syncthreads();
-    if (live_a || live_b) {
-      IstftEmit emit{fa, fb, p.hann_inv_n};
-      fft1024_stage3_complex(tid, buf2, emit);
-    }
-  }
-  __syncthreads();
-
-  // gather overlap-add over the CTA's 13 segments
-  const long long out_len = (long long)kHop * (p.n_frames - 1);
-  float* __restrict__ y = p.out + (long long)b * p.out_stride;
-  for (int idx = threadIdx.x; idx < kIstftSegs * kHop; idx += kIstftThreads) {
-    const long long n = (long long)seg0 * kHop + idx;
-    if (n >= out_len) break;
-    const int pos = (int)n + kNfft / 2;
-    int t_hi = pos >> 8;
-    if (t_hi > p.n_frames - 1) t_hi = p.n_frames - 1;
-    int t_lo = (pos - (kNfft - kHop)) >> 8;  // floor((pos - 768) / 256) == ceil((pos - 1023) / 256)
-    if (t_lo < 0) t_lo = 0;
-    float acc = 0.f, env = 0.f;
-    for (int t = t_lo; t <= t_hi; ++t) {
-      const int off = pos - (t << 8);
-      acc += frames[(t - t_first) * kFftN + off];
-      env += __ldg(p.hann_sq + off);
-    }
-    y[n] = acc / env;
   }
 }
+
+__global__ void __launch_bounds__(kIstftThreads, 8) istft_kernel(const IstftParams p) {
+  extern __shared__ __align__(16) float2 smem[];
+  float2* t1 = smem;
+  float2* t2 = smem + kTw1Size;
+  float2* buf1 = smem + kTw1Size + kTw2Size;
+  float2* buf2 = buf1 + kBuf1Size;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kTw1Size; i += kIstftThreads) t1[i] = p.t1[i];
+  for (int i = tid; i < kTw2Size; i += kIstftThreads) t2[i] = p.t2[i];
+
+  const int b = blockIdx.y;
+  const float* __restrict__ clip = p.spec + (long long)b * p.clip_stride;
+  float* __restrict__ y = p.out + (long long)b * p.out_stride;
+  // untrimmed segments g (256 samples each); outputs exist for g in [2, n_frames + 1)
+  const int g0 = 2 + blockIdx.x * p.run_segs;
+  const int g1 = min(g0 + p.run_segs, p.n_frames + 1);
+  const bool first = tid == 0;
+  const int qs[4] = {first ? 0 : tid, first ? 128 : 256 - tid, first ? 64 : 128 - tid, first ? 192 : 128 + tid};
+
+  OlaEmit ola;
+  float wsq[4][4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const float w = __ldg(p.hann_inv_n + qs[s] + 256 * a);
+      ola.wn[s][a] = w;
+      wsq[s][a] = (w * 1024.f) * (w * 1024.f);
+    }
+  float renv[4];  // 1 / (w^2 summed over four frames, frame-ascending), the interior envelope
+#pragma unroll
+  for (int s = 0; s < 4; ++s) renv[s] = 1.0f / (((wsq[s][3] + wsq[s][2]) + wsq[s][1]) + wsq[s][0]);
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+#pragma unroll
+    for (int c = 0; c < 5; ++c) ola.acc[s][c] = 0.f;
+  __syncthreads();
+
+  // frames g0 - 3 .. g1 - 1 contribute; pairs start on the even frame g0 - 4 (g0 is even)
+  int t_next = max(g0 - 4, 0);
+  for (int t = t_next; t < g1 && t < p.n_frames; t += 2) {
+    const bool live_a = true, live_b = t + 1 < p.n_frames;
+    {
+      const FrameRows fa = merged_rows(p, clip, t);
+      const FrameRows fb = live_b ? merged_rows(p, clip, t + 1) : fa;
+      float2 v[16];
+      load_inputs<0>(v, tid, fa, fb, p.plane, live_a, live_b);
+      fft1024_stage1(v, tid, t1, buf1);
+    }
+    __syncthreads();
+    fft1024_stage2(tid, t2, buf1, buf2);
+    __syncthreads();
+    fft1024_stage3_columns(tid, buf2, ola);
+    // segments t and t + 1 are complete now (no later frame reaches them)
+    emit_segments(p, ola, wsq, renv, qs, y, t, g0, g1);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      ola.acc[s][0] = ola.acc[s][2];
+      ola.acc[s][1] = ola.acc[s][3];
+      ola.acc[s][2] = ola.acc[s][4];
+      ola.acc[s][3] = 0.f;
+      ola.acc[s][4] = 0.f;
+    }
+    t_next = t + 2;
+  }
+  // when the clip ends on an even frame count the last segment (g = n_frames) is still pending
+  emit_segments(p, ola, wsq, renv, qs, y, t_next, g0, g1);
+}
+
+static int g_istft_ctas_per_sm = 8;
 
 int istft_init() {
   AST_CUDA_TRY(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIstftSmem));
+  int n = 0;
+  AST_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, istft_kernel, kIstftThreads, kIstftSmem));
+  g_istft_ctas_per_sm = n > 0 ? n : 1;
   return AST_OK;
 }
 
@@ -144,7 +207,6 @@ int launch_istft(const ast_plan* plan, const float* spec, int batch, int dim1, i
   if (n_frames < 2 || batch == 0) return AST_OK;  // 256 * (T - 1) = 0 samples
   IstftParams p;
   p.spec = spec;
-  p.batch = batch;
   p.dim1 = dim1;
   p.f_in = f_in;
   p.layout = layout;
@@ -152,13 +214,28 @@ int launch_istft(const ast_plan* plan, const float* spec, int batch, int dim1, i
   p.sec_hop = window - overlap;
   p.n_frames = n_frames;
   p.clip_stride = layout == AST_LAYOUT_FLAT ? 2LL * dim1 * f_in : 2LL * dim1 * window * f_in;
+  p.plane = (long long)(layout == AST_LAYOUT_FLAT ? dim1 : window) * f_in;
   p.out = wave_out;
   p.out_stride = out_stride;
-  p.tw = plan->d_tw;
+  p.t1 = plan->d_tw1;
+  p.t2 = plan->d_tw2;
   p.hann_inv_n = plan->d_hann_inv_n;
-  p.hann_sq = plan->d_hann_sq;
+  // run length R (even): long runs amortise the 4 halo frames, short runs fill the machine.  Pick the R
+  // in [16, 128] that minimises (frames transformed) x (wave quantisation) for this grid.
   const int segs = n_frames - 1;
-  dim3 grid((unsigned)((segs + kIstftSegs - 1) / kIstftSegs), (unsigned)batch);
+  const long long slots = (long long)plan->sm_count * g_istft_ctas_per_sm;
+  double best = 1e300;
+  int best_r = 32;
+  for (int r = 16; r <= 128; r += 2) {
+    const long long runs = (segs + r - 1) / r;
+    const long long ctas = runs * batch;
+    const double waves = (double)((ctas + slots - 1) / slots);
+    const double per_cta = r + 4;                       // frames per run incl. halo
+    const double cost = waves * per_cta;                // time ~ waves x work per CTA
+    if (cost < best * 0.999) best = cost, best_r = r;
+  }
+  p.run_segs = best_r;
+  dim3 grid((unsigned)((segs + best_r - 1) / best_r), (unsigned)batch);
   ProfileSpan span("istft_kernel", st);
   istft_kernel<<<grid, kIstftThreads, kIstftSmem, st>>>(p);
   AST_LAUNCH_CHECK("istft_kernel");

@@ -266,11 +266,10 @@ int ast_plan_create(const ast_config* cfg, ast_plan** out) {
 
   std::vector<double> hann(kNfft);
   host_hann(hann.data(), kNfft);
-  std::vector<float2> tw(kNfft);
+  std::vector<float2> tw1(kTw1Size), tw2(kTw2Size);
+  fill_twiddle_tables(tw1.data(), tw2.data());
   std::vector<float> w(kNfft), w_inv(kNfft), w_sq(kNfft);
   for (int m = 0; m < kNfft; ++m) {
-    const double a = -2.0 * M_PI * m / kNfft;
-    tw[m] = make_float2((float)std::cos(a), (float)std::sin(a));
     w[m] = (float)hann[m];
     w_inv[m] = (float)(hann[m] / kNfft);
     w_sq[m] = (float)(hann[m] * hann[m]);
@@ -309,7 +308,8 @@ int ast_plan_create(const ast_config* cfg, ast_plan** out) {
       return fail(AST_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(e)); \
     }                                                                          \
   } while (0)
-  AST_ALLOC_COPY(p->d_tw, tw.data(), sizeof(float2) * kNfft);
+  AST_ALLOC_COPY(p->d_tw1, tw1.data(), sizeof(float2) * kTw1Size);
+  AST_ALLOC_COPY(p->d_tw2, tw2.data(), sizeof(float2) * kTw2Size);
   AST_ALLOC_COPY(p->d_hann, w.data(), sizeof(float) * kNfft);
   AST_ALLOC_COPY(p->d_hann_inv_n, w_inv.data(), sizeof(float) * kNfft);
   AST_ALLOC_COPY(p->d_hann_sq, w_sq.data(), sizeof(float) * kNfft);
@@ -329,7 +329,8 @@ int ast_plan_create(const ast_config* cfg, ast_plan** out) {
 
 int ast_plan_destroy(ast_plan* p) {
   if (!p) return AST_OK;
-  cudaFree(p->d_tw);
+  cudaFree(p->d_tw1);
+  cudaFree(p->d_tw2);
   cudaFree(p->d_hann);
   cudaFree(p->d_hann_inv_n);
   cudaFree(p->d_hann_sq);

@@ -4,129 +4,182 @@
 // dataloader.normalize (dataloader.py:9-13) and get_overlap_windows (utilityFunctions.py:240-263)
 // for the STFT columns of the feature tensor.
 //
-// One group of 64 threads owns one frame pair; a 256-thread CTA runs four groups in lock step over
-// a grid-stride list of (clip, frame pair) items.  Shared memory per CTA: 8 KB twiddles +
-// 4 x (8320 B + 8192 B) exchange buffers = 74 240 B -> 3 CTAs / SM.
+// One group of 64 threads owns one frame pair (frames 2p and 2p+1 share one complex FFT, and
+// share 3/4 of their samples: 20 strided loads feed both).  A 256-thread CTA runs four groups in
+// lock step over `iters` consecutive groups of pairs of ONE clip (grid = pair tiles x clips), so all
+// per-clip bookkeeping is CTA-uniform.  Interior frames take a check-free load path; rows whose
+// destinations are all live take a select-free store path.  Shared memory per CTA: 10 KB twiddle
+// tables + 4 x (8320 B + 8192 B) exchange buffers = 76 288 B.
 #include "common.cuh"
 
 namespace ast {
 
 constexpr int kStftGroups = 4;
 constexpr int kStftThreads = kStftGroups * kFftThreads;
-constexpr size_t kStftSmem = sizeof(float2) * (kFftN + kStftGroups * (kBuf1Size + kBuf2Size));
+constexpr size_t kStftSmem = sizeof(float2) * (kTw1Size + kTw2Size + kStftGroups * (kBuf1Size + kBuf2Size));
 
 struct StftParams {
   const float* wave;
   const int32_t* lengths;
   long long max_samples, wave_stride;
-  int batch;
   int slots;            // frame slots per clip (rows of the output the kernel must cover)
   int pairs_per_clip;   // ceil(slots / 2)
-  long long items;      // batch * pairs_per_clip
-  const float2* tw;
+  int iters;            // pair groups per CTA
+  const float2* t1;
+  const float2* t2;
   const float* hann;
   int overlap;
   OutSpec out;
 };
 
+// Destination of the two frames of a pair: up to two rows each (a frame inside the overlap of two
+// sections is stored twice).  kAllLive: every present row receives data (no zero padding involved).
+template <bool kAllLive>
 struct StftEmit {
-  RowDest da, db;          // destinations of frame A / B
-  const float2* st0;       // stats row of channel 0 (mean, rstd) or nullptr
-  const float2* st1;       // stats row of channel 1
+  float* a0;
+  float* a1;
+  float* b0;
+  float* b1;            // channel-0 row bases (nullptr: absent)
+  bool la0, la1, lb0, lb1;
+  long long plane;      // floats from the channel-0 row to the channel-1 row
+  const float2* st0;    // (mean, rstd) of channel 0, or nullptr
+  const float2* st1;
+  // values arrive WITHOUT the factor 1/2 of the Hermitian separation; x = 0.5 s is exact, so
+  // fmaf(s, 0.5, -mean) rounds once, exactly like the reference's (x - mean).
   __device__ __forceinline__ void operator()(int k, float are, float aim, float bre, float bim) const {
     if (st0) {
       const float2 m0 = __ldg(st0 + k), m1 = __ldg(st1 + k);
-      are = (are - m0.x) * m0.y;
-      bre = (bre - m0.x) * m0.y;
-      aim = (aim - m1.x) * m1.y;
-      bim = (bim - m1.x) * m1.y;
+      are = fmaf(are, 0.5f, -m0.x) * m0.y;
+      bre = fmaf(bre, 0.5f, -m0.x) * m0.y;
+      aim = fmaf(aim, 0.5f, -m1.x) * m1.y;
+      bim = fmaf(bim, 0.5f, -m1.x) * m1.y;
+    } else {
+      are *= 0.5f, aim *= 0.5f, bre *= 0.5f, bim *= 0.5f;
     }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      if (i < da.n) {
-        da.row[i][k] = da.live[i] ? are : 0.f;
-        da.row[i][da.plane + k] = da.live[i] ? aim : 0.f;
-      }
-      if (i < db.n) {
-        db.row[i][k] = db.live[i] ? bre : 0.f;
-        db.row[i][db.plane + k] = db.live[i] ? bim : 0.f;
-      }
+    if (kAllLive) {
+      a0[k] = are;
+      a0[plane + k] = aim;
+      if (a1) a1[k] = are, a1[plane + k] = aim;
+      if (b0) b0[k] = bre, b0[plane + k] = bim;
+      if (b1) b1[k] = bre, b1[plane + k] = bim;
+    } else {
+      if (a0) a0[k] = la0 ? are : 0.f, a0[plane + k] = la0 ? aim : 0.f;
+      if (a1) a1[k] = la1 ? are : 0.f, a1[plane + k] = la1 ? aim : 0.f;
+      if (b0) b0[k] = lb0 ? bre : 0.f, b0[plane + k] = lb0 ? bim : 0.f;
+      if (b1) b1[k] = lb1 ? bre : 0.f, b1[plane + k] = lb1 ? bim : 0.f;
     }
   }
 };
 
-__device__ __forceinline__ float load_reflect(const float* __restrict__ x, long long i, long long len) {
+__device__ __forceinline__ float load_reflect(const float* __restrict__ x, int i, int len) {
   // torch.stft(center=True, pad_mode="reflect"): one reflection suffices because len > n_fft / 2
   if (i < 0) i = -i;
   if (i >= len) i = 2 * (len - 1) - i;
   return __ldg(x + i);
 }
 
+// rows of frame slot t (SECTIONS: the section starting at or before t, and the previous one if t is
+// still inside it; FLAT: one row)
+__device__ __forceinline__ void frame_rows(const OutSpec& o, int b, int t, int frames_b, int sections_b, float*& r0,
+                                           float*& r1, bool& l0, bool& l1) {
+  r0 = r1 = nullptr;
+  l0 = l1 = false;
+  if (o.layout == AST_LAYOUT_FLAT) {
+    r0 = o.out + ((long long)b * 2 * o.dim1 + t) * o.f_row + o.f_off;
+    l0 = t < frames_b;
+    return;
+  }
+  int s_hi = t / o.step;
+  if (s_hi > o.dim1 - 1) s_hi = o.dim1 - 1;
+  const int tau = t - s_hi * o.step;
+  if (tau < o.window) {
+    r0 = o.out + (((long long)b * o.dim1 + s_hi) * 2 * o.window + tau) * o.f_row + o.f_off;
+    l0 = (s_hi < sections_b) && (t < frames_b);
+  }
+  if (s_hi >= 1 && tau + o.step < o.window) {
+    r1 = o.out + (((long long)b * o.dim1 + s_hi - 1) * 2 * o.window + tau + o.step) * o.f_row + o.f_off;
+    l1 = (s_hi - 1 < sections_b) && (t < frames_b);
+  }
+  if (!r0) {  // keep r0 the primary row
+    r0 = r1, l0 = l1;
+    r1 = nullptr, l1 = false;
+  }
+}
+
 __global__ void __launch_bounds__(kStftThreads, 2) stft_kernel(const StftParams p) {
   extern __shared__ __align__(16) float2 smem[];
-  float2* tw = smem;
+  float2* t1 = smem;
+  float2* t2 = smem + kTw1Size;
   const int group = threadIdx.x >> 6, tid = threadIdx.x & 63;
-  float2* buf1 = smem + kFftN + group * (kBuf1Size + kBuf2Size);
+  float2* buf1 = smem + kTw1Size + kTw2Size + group * (kBuf1Size + kBuf2Size);
   float2* buf2 = buf1 + kBuf1Size;
-  for (int i = threadIdx.x; i < kFftN; i += kStftThreads) tw[i] = p.tw[i];
+  for (int i = threadIdx.x; i < kTw1Size; i += kStftThreads) t1[i] = p.t1[i];
+  for (int i = threadIdx.x; i < kTw2Size; i += kStftThreads) t2[i] = p.t2[i];
   float win[16];
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1) win[n1] = __ldg(p.hann + 64 * n1 + tid);
+
+  const int b = blockIdx.y;
+  const int len = (int)(p.lengths ? p.lengths[b] : p.max_samples);
+  const int frames_b = num_frames(len);
+  const int sections_b = p.out.layout == AST_LAYOUT_SECTIONS ? num_sections(frames_b, p.out.window, p.overlap) : 0;
+  const float* __restrict__ x = p.wave + (long long)b * p.wave_stride;
+  const float2* st0 = nullptr;
+  const float2* st1 = nullptr;
+  if (p.out.stats) {
+    st0 = p.out.stats + (long long)b * p.out.stats_clip_stride + p.out.stats_off;
+    st1 = st0 + p.out.f_stats;
+  }
+  const long long plane = (long long)(p.out.layout == AST_LAYOUT_FLAT ? p.out.dim1 : p.out.window) * p.out.f_row;
   __syncthreads();
 
-  const long long stride = (long long)gridDim.x * kStftGroups;
-  const long long rounds = (p.items + stride - 1) / stride;
-  for (long long r = 0; r < rounds; ++r) {
-    const long long item = r * stride + (long long)blockIdx.x * kStftGroups + group;
-    const bool active = item < p.items;
-    int b = 0, ta = 0, frames_b = 0, sections_b = 0;
-    bool any_live = false;
-    if (active) {
-      b = (int)(item / p.pairs_per_clip);
-      ta = 2 * (int)(item % p.pairs_per_clip);
-      const long long len = p.lengths ? p.lengths[b] : p.max_samples;
-      frames_b = num_frames(len);
-      sections_b = p.out.layout == AST_LAYOUT_SECTIONS ? num_sections(frames_b, p.out.window, p.overlap) : 0;
-      any_live = ta < frames_b;
-      if (any_live) {
-        const float* x = p.wave + (long long)b * p.wave_stride;
+  for (int it = 0; it < p.iters; ++it) {
+    const int pair = (blockIdx.x * p.iters + it) * kStftGroups + group;
+    const bool active = pair < p.pairs_per_clip;
+    const int ta = 2 * pair;
+    const bool any_live = active && ta < frames_b;
+    if (any_live) {
+      float2 v[16];
+      const int base = ta * kHop - kNfft / 2 + tid;
+      const bool interior = ta >= 2 && (ta + 1) * kHop + kNfft / 2 <= len;
+      if (interior) {
+        // frame B sample n is frame A sample n + 256: x[base + 64 j], j = 0..19, feeds both
+        const float* __restrict__ xp = x + base;
+        float xv[20];
+#pragma unroll
+        for (int j = 0; j < 20; ++j) xv[j] = __ldg(xp + 64 * j);
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) v[n1] = make_float2(xv[n1] * win[n1], xv[n1 + 4] * win[n1]);
+      } else {
         const bool live_b = ta + 1 < frames_b;
-        const long long base = (long long)ta * kHop - kNfft / 2 + tid;
-        float2 v[16];
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
-          const long long i = base + 64 * n1;
+          const int i = base + 64 * n1;
           const float xa = load_reflect(x, i, len);
           const float xb = live_b ? load_reflect(x, i + kHop, len) : 0.f;
           v[n1] = make_float2(xa * win[n1], xb * win[n1]);
         }
-        fft1024_stage1(v, tid, tw, buf1);
       }
+      fft1024_stage1(v, tid, t1, buf1);
     }
     __syncthreads();
-    if (any_live) fft1024_stage2(tid, tw, buf1, buf2);
+    if (any_live) fft1024_stage2(tid, t2, buf1, buf2);
     __syncthreads();
     if (active) {
-      StftEmit emit;
-      emit.da = row_dest(p.out, b, ta, frames_b, sections_b);
-      if (ta + 1 < p.slots) {
-        emit.db = row_dest(p.out, b, ta + 1, frames_b, sections_b);
+      float *a0, *a1, *b0 = nullptr, *b1 = nullptr;
+      bool la0, la1, lb0 = false, lb1 = false;
+      frame_rows(p.out, b, ta, frames_b, sections_b, a0, a1, la0, la1);
+      if (ta + 1 < p.slots) frame_rows(p.out, b, ta + 1, frames_b, sections_b, b0, b1, lb0, lb1);
+      const bool all_live = la0 && (la1 || !a1) && (lb0 || !b0) && (lb1 || !b1);
+      if (any_live && all_live) {
+        StftEmit<true> emit{a0, a1, b0, b1, true, true, true, true, plane, st0, st1};
+        fft1024_stage3_real_pair<false>(tid, buf2, emit);
+      } else if (any_live) {
+        StftEmit<false> emit{a0, a1, b0, b1, la0, la1, lb0, lb1, plane, st0, st1};
+        fft1024_stage3_real_pair<false>(tid, buf2, emit);
       } else {
-        emit.db.n = 0;
-        emit.db.plane = 0;
-      }
-      emit.st0 = nullptr;
-      emit.st1 = nullptr;
-      if (p.out.stats) {
-        emit.st0 = p.out.stats + (long long)b * p.out.stats_clip_stride + p.out.stats_off;
-        emit.st1 = emit.st0 + p.out.f_stats;
-      }
-      if (any_live) {
-        fft1024_stage3_real_pair(tid, buf2, emit);
-      } else {
-        // both frames lie past the clip: the rows exist in the output and must be zeros
-        emit.da.live[0] = emit.da.live[1] = emit.db.live[0] = emit.db.live[1] = false;
-        emit.st0 = nullptr;
+        // both frames lie past the clip: their rows exist in the output and must be zeros
+        StftEmit<false> emit{a0, a1, b0, b1, false, false, false, false, plane, nullptr, nullptr};
         for (int k = tid; k < kFStft; k += kFftThreads) emit(k, 0.f, 0.f, 0.f, 0.f);
       }
     }
@@ -150,20 +203,25 @@ int launch_stft(const ast_plan* plan, const float* wave, const int32_t* lengths,
   p.lengths = lengths;
   p.max_samples = max_samples;
   p.wave_stride = wave_stride;
-  p.batch = batch;
   p.slots = frame_slots(out.layout, out.dim1, out.window, out.step);
   p.pairs_per_clip = (p.slots + 1) / 2;
-  p.items = (long long)batch * p.pairs_per_clip;
-  p.tw = plan->d_tw;
+  p.t1 = plan->d_tw1;
+  p.t2 = plan->d_tw2;
   p.hann = plan->d_hann;
   p.overlap = out.window - out.step;
   p.out = out;
-  if (p.items == 0) return AST_OK;
-  long long blocks = (p.items + kStftGroups - 1) / kStftGroups;
-  const long long cap = (long long)plan->sm_count * g_stft_ctas_per_sm;  // persistent: every CTA resident
-  if (blocks > cap) blocks = cap;
+  if (p.pairs_per_clip == 0 || batch == 0) return AST_OK;
+  if (max_samples >= (1LL << 30)) return fail(AST_ERR_INVALID_ARG, "clips longer than 2^30 samples are not supported");
+  // pair groups per CTA: aim at ~4 CTAs per resident slot over the whole grid, at most 8 groups per CTA
+  const long long groups_per_clip = (p.pairs_per_clip + kStftGroups - 1) / kStftGroups;
+  const long long slots_total = (long long)plan->sm_count * g_stft_ctas_per_sm * 4;
+  long long iters = (groups_per_clip * batch + slots_total - 1) / slots_total;
+  if (iters < 1) iters = 1;
+  if (iters > 8) iters = 8;
+  p.iters = (int)iters;
+  dim3 grid((unsigned)((groups_per_clip + iters - 1) / iters), (unsigned)batch);
   ProfileSpan span("stft_kernel", st);
-  stft_kernel<<<(unsigned)blocks, kStftThreads, kStftSmem, st>>>(p);
+  stft_kernel<<<grid, kStftThreads, kStftSmem, st>>>(p);
   AST_LAUNCH_CHECK("stft_kernel");
   return AST_OK;
 }

@@ -32,6 +32,9 @@ def test_complex_fft1024(emul):
     assert bad == 0  # every output index written exactly once
     ref = np.fft.fft(z.astype(np.complex128))
     assert np.abs(out - ref).max() < 2e-6 * np.abs(ref).max()
+    out2 = np.zeros(1024, dtype=np.complex64)
+    assert emul.emul_fft1024_columns(_p(z), _p(out2)) == 0
+    assert np.array_equal(out, out2)
 
 
 def test_real_pair_forward(emul):
@@ -53,6 +56,7 @@ def test_real_pair_inverse(emul):
     rng = np.random.default_rng(2)
     xa = (rng.standard_normal(513) + 1j * rng.standard_normal(513)).astype(np.complex64)
     xb = (rng.standard_normal(513) + 1j * rng.standard_normal(513)).astype(np.complex64)
+    assert emul.emul_pack_check(_p(xa), _p(xb)) == 0
     fa = np.zeros(1024, dtype=np.float32)
     fb = np.zeros(1024, dtype=np.float32)
     emul.emul_irfft_pair(_p(xa), _p(xb), _p(fa), _p(fb))
