@@ -139,6 +139,8 @@ struct ast_plan {
   float* d_hann_sq;     // Hann^2 (iSTFT envelope)
   float* d_cqt_kernel;  // [256][24] base time-domain CQT kernel (12 re then 12 im columns)
   float* d_cqt_scale;   // [7][12] per octave / bin scale sqrt(2^i) / sqrt(length_k)
+  float* d_dec_strip_hi;  // decimator Toeplitz strip, TF32 hi part (smem image, decimate.cu)
+  float* d_dec_strip_lo;  // ... and the TF32 residual
 };
 
 namespace ast {
@@ -161,6 +163,9 @@ int launch_stats_accumulate(const double* clip_stats, const int32_t* group_ids, 
                             double* acc, double* counts, cudaStream_t st);
 int upload_decimator_taps(const float* taps_scaled);
 int stft_init();   // opt-in shared memory + occupancy query (once per device)
+int decimate_init();
+void host_decimator_strip(const double* taps_scaled, float* strip_hi, float* strip_lo);  // 2 x 2048 floats
+void set_tc_decimator(int on);
 int istft_init();  // into __constant__ memory of decimate.cu
 
 // octave buffer layout inside the CQT workspace (floats, per clip): buffers 1..6, each padded

@@ -12,6 +12,7 @@
 #include <complex>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -315,10 +316,21 @@ int ast_plan_create(const ast_config* cfg, ast_plan** out) {
   AST_ALLOC_COPY(p->d_hann_sq, w_sq.data(), sizeof(float) * kNfft);
   AST_ALLOC_COPY(p->d_cqt_kernel, kmat.data(), sizeof(float) * kmat.size());
   AST_ALLOC_COPY(p->d_cqt_scale, scale.data(), sizeof(float) * scale.size());
+  {
+    std::vector<double> taps_scaled(kDecTaps);
+    for (int i = 0; i < kDecTaps; ++i) taps_scaled[i] = taps[i] * std::sqrt(2.0);
+    std::vector<float> strip_hi(2048), strip_lo(2048);
+    host_decimator_strip(taps_scaled.data(), strip_hi.data(), strip_lo.data());
+    AST_ALLOC_COPY(p->d_dec_strip_hi, strip_hi.data(), sizeof(float) * 2048);
+    AST_ALLOC_COPY(p->d_dec_strip_lo, strip_lo.data(), sizeof(float) * 2048);
+  }
 #undef AST_ALLOC_COPY
   int rc = upload_decimator_taps(taps_f.data());
   if (rc == AST_OK) rc = stft_init();
   if (rc == AST_OK) rc = istft_init();
+  if (rc == AST_OK) rc = decimate_init();
+  if (const char* env = std::getenv("AST_DECIMATOR"))  // diagnostic A/B switch: "fma" selects the FMA-pipe kernel
+    set_tc_decimator(std::strcmp(env, "fma") != 0);
   if (rc != AST_OK) {
     ast_plan_destroy(p);
     return rc;
@@ -336,6 +348,8 @@ int ast_plan_destroy(ast_plan* p) {
   cudaFree(p->d_hann_sq);
   cudaFree(p->d_cqt_kernel);
   cudaFree(p->d_cqt_scale);
+  cudaFree(p->d_dec_strip_hi);
+  cudaFree(p->d_dec_strip_lo);
   delete p;
   return AST_OK;
 }
