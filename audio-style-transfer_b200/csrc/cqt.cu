@@ -113,8 +113,14 @@ __global__ void __launch_bounds__(kCqtThreads) cqt_kernel(const CqtParams p) {
   }
 }
 
+static int g_use_tc_cqt = 1;
+void set_tc_cqt(int on) { g_use_tc_cqt = on; }
+bool use_tc_cqt() { return g_use_tc_cqt != 0; }
+
 int launch_cqt(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
                long long wave_stride, const float* ws, long long ws_clip_stride, const OutSpec& out, cudaStream_t st) {
+  if (g_use_tc_cqt)
+    return launch_cqt_tc(plan, wave, lengths, batch, max_samples, wave_stride, ws, ws_clip_stride, out, st);
   CqtParams p;
   p.wave = wave;
   p.wave_stride = wave_stride;

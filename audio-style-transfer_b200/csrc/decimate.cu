@@ -163,6 +163,51 @@ struct DecimateTcParams {
   const float* strip_lo;
 };
 
+// what one tile reads / writes
+struct DecTile {
+  const float* x;
+  float* y;
+  int len_in, len_out, row0;
+  bool live;  // false: the tile lies past the clip's end (ragged batch), nothing to do
+};
+
+__device__ __forceinline__ DecTile decode_dec_tile(const DecimateTcParams& p, int tile) {
+  using namespace tc;
+  DecTile t;
+  const int b = tile / p.tiles_per_clip;
+  t.row0 = (tile - b * p.tiles_per_clip) * kM;
+  const long long len0 = p.lengths ? p.lengths[b] : p.max_samples;
+  t.len_in = (int)((len0 + (1LL << p.in_octave) - 1) >> p.in_octave);
+  t.len_out = (t.len_in + 1) >> 1;
+  t.live = t.row0 * kNB < t.len_out;
+  t.x = p.in + (long long)b * p.in_stride;
+  t.y = p.out + (long long)b * p.out_stride;
+  return t;
+}
+
+// issue the global loads of a tile's signal segment: chunk u -> row R = u / 16, chunk e = u % 16
+__device__ __forceinline__ void prefetch_dec_tile(const DecTile& t, bool vec_ok, int tid, float4 (&v)[tc::kLoadIters]) {
+  using namespace tc;
+  const int s_base = kRowHop * t.row0 - kDecHalf;
+#pragma unroll
+  for (int i = 0; i < kLoadIters; ++i) {
+    const int u = tid + i * kThreads;
+    const int R = u >> 4, e = u & 15;
+    const int s = s_base + kRowHop * R + 4 * e;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (u < kRowsUsed * kCh && t.live) {
+      if (s >= 0 && s + 3 < t.len_in && vec_ok) {
+        v[i] = __ldg(reinterpret_cast<const float4*>(t.x + s));
+      } else {
+        if (s >= 0 && s < t.len_in) v[i].x = __ldg(t.x + s);
+        if (s + 1 >= 0 && s + 1 < t.len_in) v[i].y = __ldg(t.x + s + 1);
+        if (s + 2 >= 0 && s + 2 < t.len_in) v[i].z = __ldg(t.x + s + 2);
+        if (s + 3 >= 0 && s + 3 < t.len_in) v[i].w = __ldg(t.x + s + 3);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(tc::kThreads, 2) decimate2_tc_kernel(const DecimateTcParams p) {
   using namespace tc;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -191,35 +236,13 @@ __global__ void __launch_bounds__(tc::kThreads, 2) decimate2_tc_kernel(const Dec
 
   uint32_t phase = 0;
   const int total = p.tiles_per_clip * p.batch;
+  // software pipeline: the next tile's global loads are in flight while the tensor core works on this one
+  float4 v[kLoadIters];
+  DecTile cur = decode_dec_tile(p, min((int)blockIdx.x, total - 1));
+  prefetch_dec_tile(cur, p.vec_ok, tid, v);
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const int b = tile / p.tiles_per_clip;
-    const int row0 = (tile - b * p.tiles_per_clip) * kM;
-    const long long len0 = p.lengths ? p.lengths[b] : p.max_samples;
-    const int len_in = (int)((len0 + (1LL << p.in_octave) - 1) >> p.in_octave);
-    const int len_out = (len_in + 1) >> 1;
-    if (row0 * kNB >= len_out) continue;  // CTA-uniform
-    const float* __restrict__ x = p.in + (long long)b * p.in_stride;
-
-    // ---- stage the signal segment: chunk u -> (row R = u / 16, chunk e = u % 16) -> slot [e][R]
-    const int s_base = kRowHop * row0 - kDecHalf;
-    float4 v[kLoadIters];
-#pragma unroll
-    for (int i = 0; i < kLoadIters; ++i) {  // all loads first: ~34 KB in flight per CTA
-      const int u = tid + i * kThreads;
-      const int R = u >> 4, e = u & 15;
-      const int s = s_base + kRowHop * R + 4 * e;
-      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (u < kRowsUsed * kCh) {
-        if (s >= 0 && s + 3 < len_in && p.vec_ok) {
-          v[i] = __ldg(reinterpret_cast<const float4*>(x + s));
-        } else {
-          if (s >= 0 && s < len_in) v[i].x = __ldg(x + s);
-          if (s + 1 >= 0 && s + 1 < len_in) v[i].y = __ldg(x + s + 1);
-          if (s + 2 >= 0 && s + 2 < len_in) v[i].z = __ldg(x + s + 2);
-          if (s + 3 >= 0 && s + 3 < len_in) v[i].w = __ldg(x + s + 3);
-        }
-      }
-    }
+    const DecTile t = cur;
+    // ---- split into TF32 hi / lo and store in chunk-column order: slot [e][R]
 #pragma unroll
     for (int i = 0; i < kLoadIters; ++i) {
       const int u = tid + i * kThreads;
@@ -242,7 +265,7 @@ __global__ void __launch_bounds__(tc::kThreads, 2) decimate2_tc_kernel(const Dec
 
     // ---- 56 K-steps x 3 split terms.  Warp 0 runs the issue code converged (descriptors are warp-uniform,
     // offsets compile-time constants after unrolling); one elected lane issues.
-    if (warp == 0) {
+    if (warp == 0 && t.live) {
       umma::fence_after_thread_sync();
       if (umma::elect_one_sync()) {
         const uint64_t da_hi0 = umma::smem_desc(a_hi_addr, kRT * 16, 128);
@@ -263,6 +286,13 @@ __global__ void __launch_bounds__(tc::kThreads, 2) decimate2_tc_kernel(const Dec
       }
     }
     __syncwarp();
+
+    if (tile + (int)gridDim.x < total) {
+      cur = decode_dec_tile(p, tile + gridDim.x);
+      prefetch_dec_tile(cur, p.vec_ok, tid, v);
+    }
+    if (!t.live) continue;  // CTA-uniform
+
     umma::mbar_wait(mbar, phase);
     phase ^= 1;
     umma::fence_after_thread_sync();
@@ -286,16 +316,16 @@ __global__ void __launch_bounds__(tc::kThreads, 2) decimate2_tc_kernel(const Dec
       for (int c = 0; c < 32; ++c) acc[c] += m1[c];
     }
     umma::fence_before_thread_sync();
-    const int j0 = (row0 + warp * 32 + lane) * kNB;
-    float* __restrict__ y = p.out + (long long)b * p.out_stride + j0;
-    if (j0 + kNB <= len_out) {
+    const int j0 = (t.row0 + warp * 32 + lane) * kNB;
+    float* __restrict__ y = t.y + j0;
+    if (j0 + kNB <= t.len_out) {
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         reinterpret_cast<float4*>(y)[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
     } else {
 #pragma unroll
       for (int c = 0; c < kNB; ++c)
-        if (j0 + c < len_out) y[c] = acc[c];
+        if (j0 + c < t.len_out) y[c] = acc[c];
     }
   }
   umma::fence_before_thread_sync();

@@ -317,6 +317,17 @@ int ast_plan_create(const ast_config* cfg, ast_plan** out) {
   AST_ALLOC_COPY(p->d_cqt_kernel, kmat.data(), sizeof(float) * kmat.size());
   AST_ALLOC_COPY(p->d_cqt_scale, scale.data(), sizeof(float) * scale.size());
   {
+    std::vector<double> kd((size_t)kCqtNfft * kCqtCols);
+    for (int n = 0; n < kCqtNfft; ++n)
+      for (int j = 0; j < kBinsPerOctave; ++j) {
+        kd[(size_t)n * kCqtCols + j] = k_re[j * kCqtNfft + n];
+        kd[(size_t)n * kCqtCols + kBinsPerOctave + j] = k_im[j * kCqtNfft + n];
+      }
+    std::vector<float> images(cqt_tc_image_floats());
+    host_cqt_tc_images(kd.data(), images.data());
+    AST_ALLOC_COPY(p->d_cqt_tc_images, images.data(), sizeof(float) * images.size());
+  }
+  {
     std::vector<double> taps_scaled(kDecTaps);
     for (int i = 0; i < kDecTaps; ++i) taps_scaled[i] = taps[i] * std::sqrt(2.0);
     std::vector<float> strip_hi(2048), strip_lo(2048);
@@ -329,6 +340,9 @@ int ast_plan_create(const ast_config* cfg, ast_plan** out) {
   if (rc == AST_OK) rc = stft_init();
   if (rc == AST_OK) rc = istft_init();
   if (rc == AST_OK) rc = decimate_init();
+  if (rc == AST_OK) rc = cqt_tc_init();
+  if (const char* env = std::getenv("AST_CQT"))  // diagnostic A/B switch: "fma" selects the FMA-pipe projection
+    set_tc_cqt(std::strcmp(env, "fma") != 0);
   if (const char* env = std::getenv("AST_DECIMATOR"))  // diagnostic A/B switch: "fma" selects the FMA-pipe kernel
     set_tc_decimator(std::strcmp(env, "fma") != 0);
   if (rc != AST_OK) {
@@ -348,6 +362,7 @@ int ast_plan_destroy(ast_plan* p) {
   cudaFree(p->d_hann_sq);
   cudaFree(p->d_cqt_kernel);
   cudaFree(p->d_cqt_scale);
+  cudaFree(p->d_cqt_tc_images);
   cudaFree(p->d_dec_strip_hi);
   cudaFree(p->d_dec_strip_lo);
   delete p;
