@@ -36,6 +36,9 @@ void profile_mark(const char* name, cudaStream_t st, bool begin) {
   }
 }
 
+static int g_overlap_streams = 1;  // AST_OVERLAP=0 serialises the two branches on the caller's stream
+void set_overlap_streams(int on) { g_overlap_streams = on; }
+
 static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 struct Workspace {
@@ -166,14 +169,32 @@ int ast_features_forward(const ast_plan* plan, const float* wave, const int32_t*
   o.stats = table;
   o.stats_clip_stride = stats_per_clip ? 2 * kFTotal : 0;
   o.stats_off = 0;
-  rc = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st);
-  if (rc != AST_OK) return rc;
+  OutSpec oq = o;
+  oq.f_off = kFStft;
+  oq.stats_off = kFStft;
   const long long ws_stride = cqt_ws_clip_stride(max_samples);
-  rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, st);
-  if (rc != AST_OK) return rc;
-  o.f_off = kFStft;
-  o.stats_off = kFStft;
-  return launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, o, st);
+  if (!g_overlap_streams || profile_on()) {
+    rc = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st);
+    if (rc != AST_OK) return rc;
+    rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, st);
+    if (rc != AST_OK) return rc;
+    return launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, oq, st);
+  }
+  // The STFT kernel lives on the FP32 pipes, the decimator + CQT projection on the tensor pipe, and they write
+  // disjoint columns of the same rows: fork the CQT branch onto the plan's side stream and join afterwards.
+  cudaEvent_t fork_ev, join_ev;
+  AST_CUDA_TRY(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+  AST_CUDA_TRY(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming));
+  AST_CUDA_TRY(cudaEventRecord(fork_ev, st));
+  AST_CUDA_TRY(cudaStreamWaitEvent(plan->side_stream, fork_ev, 0));
+  rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, plan->side_stream);
+  if (rc == AST_OK) rc = launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, oq, plan->side_stream);
+  int rc2 = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st);
+  cudaEventRecord(join_ev, plan->side_stream);
+  cudaStreamWaitEvent(st, join_ev, 0);
+  cudaEventDestroy(fork_ev);  // released by the runtime once the recorded work has completed
+  cudaEventDestroy(join_ev);
+  return rc != AST_OK ? rc : rc2;
 }
 
 int ast_istft_forward(const ast_plan* plan, const float* spec, int32_t batch, int32_t dim1, int32_t f_in, int32_t layout,

@@ -139,6 +139,7 @@ struct ast_plan {
   float* d_hann_sq;     // Hann^2 (iSTFT envelope)
   float* d_cqt_kernel;  // [256][24] base time-domain CQT kernel (12 re then 12 im columns)
   float* d_cqt_scale;   // [7][12] per octave / bin scale sqrt(2^i) / sqrt(length_k)
+  cudaStream_t side_stream;  // non-blocking stream for the tensor-pipe branch of ast_features_forward
   float* d_cqt_tc_images;  // CQT kernel as TF32 hi / lo B-operand images per pass (cqt_tc.cu)
   float* d_dec_strip_hi;  // decimator Toeplitz strip, TF32 hi part (smem image, decimate.cu)
   float* d_dec_strip_lo;  // ... and the TF32 residual
@@ -171,6 +172,7 @@ void host_cqt_tc_images(const double* kmat_256x24, float* images);
 int launch_cqt_tc(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
                   long long wave_stride, const float* ws, long long ws_clip_stride, const OutSpec& out, cudaStream_t st);
 void set_tc_cqt(int on);
+void set_overlap_streams(int on);
 bool use_tc_cqt();
 void host_decimator_strip(const double* taps_scaled, float* strip_hi, float* strip_lo);  // 2 x 2048 floats
 void set_tc_decimator(int on);

@@ -17,6 +17,11 @@
 // the hi*hi terms are spread over four accumulators (8 steps each) and the cross terms go to a fifth;
 // the epilogue sums them in registers, applies the per-bin scale and (x - mean) * rstd and scatters to the
 // flat / section layout (columns 513..596).
+//
+// 256 threads: all eight warps stage (8 chunks per thread per pass, addresses advance by constant steps),
+// warp 0 issues the MMAs, and in the epilogue warps 0-3 write the real plane and warps 4-7 the imaginary
+// plane of their TMEM lane quadrant.  The global loads of the next (tile, pass) are issued before waiting
+// for the current MMAs (register prefetch); B images are double-buffered with cp.async.
 #include <cstring>
 #include <vector>
 
@@ -31,12 +36,12 @@ constexpr int kPasses = 4;              // 64-sample slices of the 256-sample wi
 constexpr int kPassChunks = 16;         // 16-byte chunks per slice
 constexpr int kKStepsPerPass = 8;
 constexpr int kRT = 145;                // rows per chunk column (>= 143, = 1 mod 8: conflict-free transposed stores)
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
 constexpr int kAFloats = kPassChunks * kRT * 4;           // 9280 floats = 37 120 B per split term
 constexpr int kBFloats = kKStepsPerPass * 2 * kN * 4;     // 2048 floats = 8 KB per split term per pass
 constexpr int kMainAcc = 4;
 constexpr int kTmemCols = 256;
-constexpr int kMaxStage = (kM * kPassChunks + kThreads - 1) / kThreads;  // 16 chunks per thread at most
+constexpr int kStage = kM * kPassChunks / kThreads;       // 8 chunks per thread per pass at most
 constexpr size_t kSmem = sizeof(float) * (2 * kAFloats + 4 * kBFloats) + 64;  // A hi/lo + double-buffered B hi/lo
 }  // namespace cqt_tc
 
@@ -55,89 +60,90 @@ struct CqtTcParams {
   OutSpec out;
 };
 
-// what one (tile, pass) work item reads
-struct PassCtx {
-  const float* x;   // octave signal of the clip
-  int len;          // its valid length
-  int s_base;       // first sample of the slice
-  int hop, m, oct;  // m = hop / 4 chunks per frame hop
-  int n_chunks;     // chunks to stage
+// One thread's share of a (tile, pass) slice: chunk i (0..n-1) is read at src + i * src_step (samples) and
+// stored at slot + i * slot_step (16-byte units).
+struct StagePlan {
+  const float* x;
+  int len;
+  int s0, src_step;
+  int slot0, slot_step;
+  int n;          // chunks this thread stages
+  int oct, m;
   bool vec_ok;
+  bool interior;  // whole slice inside [0, len): no bounds checks
 };
 
-__device__ __forceinline__ PassCtx decode_pass(const CqtTcParams& p, int tile, int pass) {
+__device__ __forceinline__ StagePlan plan_stage(const CqtTcParams& p, int tile, int pass, int tid) {
   using namespace cqt_tc;
-  PassCtx c;
+  StagePlan s;
   const int tiles_per_clip = p.tiles_per_clip_oct * kOctaves;
   const int b = tile / tiles_per_clip;
   const int rem = tile - b * tiles_per_clip;
-  c.oct = rem / p.tiles_per_clip_oct;
-  const int t0 = (rem - c.oct * p.tiles_per_clip_oct) * kM;
+  s.oct = rem / p.tiles_per_clip_oct;
+  const int t0 = (rem - s.oct * p.tiles_per_clip_oct) * kM;
   const long long len0 = p.lengths ? p.lengths[b] : p.max_samples;
-  c.hop = kHop >> c.oct;
-  c.m = c.hop >> 2;
-  c.len = (int)((len0 + (1LL << c.oct) - 1) >> c.oct);
-  c.x = c.oct == 0 ? p.wave + (long long)b * p.wave_stride : p.ws + (long long)b * p.ws_clip_stride + p.oct_off[c.oct];
-  c.vec_ok = c.oct == 0 ? p.vec_ok : true;
-  c.s_base = t0 * c.hop - kCqtNfft / 2 + 64 * pass;
-  c.n_chunks = c.m >= kPassChunks ? kM * kPassChunks : (kM - 1) * c.m + kPassChunks;
-  return c;
+  const int hop = kHop >> s.oct;
+  s.m = hop >> 2;
+  s.len = (int)((len0 + (1LL << s.oct) - 1) >> s.oct);
+  s.x = s.oct == 0 ? p.wave + (long long)b * p.wave_stride : p.ws + (long long)b * p.ws_clip_stride + p.oct_off[s.oct];
+  s.vec_ok = s.oct == 0 ? p.vec_ok : true;
+  const int s_base = t0 * hop - kCqtNfft / 2 + 64 * pass;
+  int span;  // samples covered by the slice
+  if (s.m >= kPassChunks) {
+    // chunk u = tid + 256 i -> row r = (tid >> 4) + 16 i, chunk c' = tid & 15: sample r hop + 4 c', slot [c'][r]
+    s.s0 = s_base + (tid >> 4) * hop + 4 * (tid & 15);
+    s.src_step = 16 * hop;
+    s.slot0 = (tid & 15) * kRT + (tid >> 4);
+    s.slot_step = 16;
+    s.n = kStage;
+    span = (kM - 1) * hop + 64;
+  } else {
+    // contiguous chunk u = tid + 256 i -> row R = u / m, column e = u % m (m divides 256): slot [e][R]
+    const int lg = 6 - s.oct;  // log2(m)
+    s.s0 = s_base + 4 * tid;
+    s.src_step = 4 * kThreads;
+    s.slot0 = (tid & (s.m - 1)) * kRT + (tid >> lg);
+    s.slot_step = kThreads >> lg;
+    const int n_chunks = (kM - 1) * s.m + kPassChunks;
+    s.n = tid < n_chunks ? (n_chunks - tid + kThreads - 1) / kThreads : 0;
+    span = 4 * n_chunks;
+  }
+  s.interior = s_base >= 0 && s_base + span <= s.len && s.vec_ok;
+  return s;
 }
 
-// issue the global loads of one slice (octaves 0-2: chunk u = 16 r + c' at sample r hop + 4 c'; octaves 3-6:
-// contiguous chunk u); zeros outside [0, len) = librosa.stft(pad_mode="constant")
-__device__ __forceinline__ void prefetch_slice(const PassCtx& c, int tid, float4 (&v)[cqt_tc::kMaxStage]) {
+__device__ __forceinline__ void prefetch_slice(const StagePlan& s, float4 (&v)[cqt_tc::kStage]) {
   using namespace cqt_tc;
+  if (s.interior) {
 #pragma unroll
-  for (int i = 0; i < kMaxStage; ++i) {
-    const int u = tid + i * kThreads;
-    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (u < c.n_chunks) {
-      const int s = c.s_base + (c.m >= kPassChunks ? (u >> 4) * c.hop + 4 * (u & 15) : 4 * u);
-      if (s >= 0 && s + 3 < c.len && c.vec_ok) {
-        v[i] = __ldg(reinterpret_cast<const float4*>(c.x + s));
-      } else {
-        if (s >= 0 && s < c.len) v[i].x = __ldg(c.x + s);
-        if (s + 1 >= 0 && s + 1 < c.len) v[i].y = __ldg(c.x + s + 1);
-        if (s + 2 >= 0 && s + 2 < c.len) v[i].z = __ldg(c.x + s + 2);
-        if (s + 3 >= 0 && s + 3 < c.len) v[i].w = __ldg(c.x + s + 3);
-      }
-    }
+    for (int i = 0; i < kStage; ++i)
+      if (i < s.n) v[i] = __ldg(reinterpret_cast<const float4*>(s.x + s.s0 + i * s.src_step));
+  } else {
+#pragma unroll
+    for (int i = 0; i < kStage; ++i)
+      if (i < s.n) v[i] = umma::load4_zero_ext(s.x, s.s0 + i * s.src_step, s.len, s.vec_ok);
   }
 }
 
-// split into TF32 hi / lo and store in chunk-column order
-__device__ __forceinline__ void store_slice(const PassCtx& c, int tid, const float4 (&v)[cqt_tc::kMaxStage], float* a_hi,
-                                            float* a_lo) {
+__device__ __forceinline__ void store_slice(const StagePlan& s, const float4 (&v)[cqt_tc::kStage], float* a_hi, float* a_lo) {
   using namespace cqt_tc;
 #pragma unroll
-  for (int i = 0; i < kMaxStage; ++i) {
-    const int u = tid + i * kThreads;
-    if (u < c.n_chunks) {
-      int slot;
-      if (c.m >= kPassChunks) {
-        slot = (u & 15) * kRT + (u >> 4);                       // [c'][r]
-      } else {
-        const int R = u >> (6 - c.oct), e = u & (c.m - 1);      // [e][R]; m = 64 >> oct
-        slot = e * kRT + R;
-      }
+  for (int i = 0; i < kStage; ++i)
+    if (i < s.n) {
       float4 h, l;
-      h.x = __uint_as_float(umma::tf32_trunc_bits(__float_as_uint(v[i].x)));
-      h.y = __uint_as_float(umma::tf32_trunc_bits(__float_as_uint(v[i].y)));
-      h.z = __uint_as_float(umma::tf32_trunc_bits(__float_as_uint(v[i].z)));
-      h.w = __uint_as_float(umma::tf32_trunc_bits(__float_as_uint(v[i].w)));
-      l.x = v[i].x - h.x, l.y = v[i].y - h.y, l.z = v[i].z - h.z, l.w = v[i].w - h.w;  // exact
-      reinterpret_cast<float4*>(a_hi)[slot] = h;
-      reinterpret_cast<float4*>(a_lo)[slot] = l;
+      umma::split_tf32(v[i], h, l);
+      reinterpret_cast<float4*>(a_hi)[s.slot0 + i * s.slot_step] = h;
+      reinterpret_cast<float4*>(a_lo)[s.slot0 + i * s.slot_step] = l;
     }
-  }
 }
 
 // asynchronous copy of one pass's B images (hi then lo, 16 KB) into a B buffer
 __device__ __forceinline__ void copy_b_async(const CqtTcParams& p, int pass, int tid, float* b_buf) {
   using namespace cqt_tc;
   const float4* src = reinterpret_cast<const float4*>(p.bmat) + (size_t)pass * 2 * (kBFloats / 4);
-  for (int i = tid; i < 2 * kBFloats / 4; i += kThreads) umma::cp_async_16(reinterpret_cast<float4*>(b_buf) + i, src + i);
+#pragma unroll
+  for (int i = 0; i < 2 * kBFloats / 4 / kThreads; ++i)
+    umma::cp_async_16(reinterpret_cast<float4*>(b_buf) + tid + i * kThreads, src + tid + i * kThreads);
 }
 
 __global__ void __launch_bounds__(cqt_tc::kThreads, 2) cqt_tc_kernel(const CqtTcParams p) {
@@ -162,24 +168,20 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 2) cqt_tc_kernel(const CqtTc
 
   uint32_t phase = 0;
   const int tiles_per_clip = p.tiles_per_clip_oct * kOctaves;
-  const int total = tiles_per_clip * p.batch;
-  if ((int)blockIdx.x >= total) {  // (grid never exceeds the tile count; kept for safety)
-    __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem_base, kTmemCols);
-    return;
-  }
+  const int total = tiles_per_clip * p.batch;  // gridDim.x <= total
 
   // software pipeline: the global loads of item (tile, pass) + 1 are in flight while item (tile, pass) runs
-  float4 v[kMaxStage];
-  PassCtx cur = decode_pass(p, blockIdx.x, 0);
-  prefetch_slice(cur, tid, v);
+  float4 v[kStage];
+  StagePlan cur = plan_stage(p, blockIdx.x, 0, tid);
+  prefetch_slice(cur, v);
   copy_b_async(p, 0, tid, b_buf0);
   int item = 0;
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
     for (int pass = 0; pass < kPasses; ++pass, ++item) {
       float* b_cur = (item & 1) ? b_buf1 : b_buf0;
       float* b_nxt = (item & 1) ? b_buf0 : b_buf1;
-      store_slice(cur, tid, v, a_hi, a_lo);   // waits for this item's loads
+      const int oct = cur.oct, m = cur.m;
+      store_slice(cur, v, a_hi, a_lo);        // waits for this item's loads
       umma::cp_async_wait_all();              // this item's B images have landed
       umma::fence_proxy_async_smem();
       umma::fence_before_thread_sync();
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 2) cqt_tc_kernel(const CqtTc
         umma::fence_after_thread_sync();
         if (umma::elect_one_sync()) {
           const uint32_t b_hi_addr = umma::smem_u32(b_cur), b_lo_addr = umma::smem_u32(b_cur + kBFloats);
-          const uint32_t lbo = cur.m == 1 ? 16u : (uint32_t)kRT * 16u;
+          const uint32_t lbo = m == 1 ? 16u : (uint32_t)kRT * 16u;
           const uint64_t da_hi0 = umma::smem_desc(a_hi_addr, lbo, 128);
           const uint64_t da_lo0 = umma::smem_desc(a_lo_addr, lbo, 128);
           const uint64_t db_hi0 = umma::smem_desc(b_hi_addr, kN * 16, 128);
@@ -198,12 +200,12 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 2) cqt_tc_kernel(const CqtTc
           for (int ks = 0; ks < kKStepsPerPass; ++ks) {
             const int c = 2 * ks;  // first window chunk of the K-step inside this slice
             int a_units;           // start-address offset in 16-byte units
-            if (cur.m >= kPassChunks) {
+            if (m >= kPassChunks) {
               a_units = c * kRT;
-            } else if (cur.m == 1) {
+            } else if (m == 1) {
               a_units = c;
             } else {
-              const int d = c >> (6 - cur.oct), e = c & (cur.m - 1);  // m = 64 >> oct is a power of two
+              const int d = c >> (6 - oct), e = c & (m - 1);  // m = 64 >> oct is a power of two
               a_units = d + e * kRT;
             }
             const uint64_t a_off = (uint64_t)a_units, b_off = (uint64_t)(ks * 2 * kN);
@@ -219,17 +221,15 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 2) cqt_tc_kernel(const CqtTc
       __syncwarp();
 
       // prefetch the next work item while the tensor core runs
-      const PassCtx this_ctx = cur;
       {
         int ntile = tile, npass = pass + 1;
         if (npass == kPasses) npass = 0, ntile = tile + gridDim.x;
         if (ntile < total) {
-          cur = decode_pass(p, ntile, npass);
-          prefetch_slice(cur, tid, v);
+          cur = plan_stage(p, ntile, npass, tid);
+          prefetch_slice(cur, v);
           copy_b_async(p, npass, tid, b_nxt);
         }
       }
-      (void)this_ctx;
 
       // the MMAs read this item's smem: wait before the next store_slice overwrites it / before the epilogue
       umma::mbar_wait(mbar, phase);
@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 2) cqt_tc_kernel(const CqtTc
       umma::fence_after_thread_sync();
     }
 
-    // ---- epilogue: thread owns frame t = t0 + 32 warp + lane of this tile
+    // ---- epilogue: warps 0-3 write the real plane, warps 4-7 the imaginary plane; thread owns frame
+    //      t = t0 + 32 (warp & 3) + lane of this tile
     const int b = tile / tiles_per_clip;
     const int rem = tile - b * tiles_per_clip;
     const int oct = rem / p.tiles_per_clip_oct;
@@ -245,43 +246,41 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 2) cqt_tc_kernel(const CqtTc
     const long long len0 = p.lengths ? p.lengths[b] : p.max_samples;
     const int frames_b = num_frames(len0);
     const int sections_b = p.out.layout == AST_LAYOUT_SECTIONS ? num_sections(frames_b, p.out.window, p.overlap) : 0;
-    float acc[32];
+    const int part = warp >> 2;  // 0: real (columns 0..11), 1: imaginary (columns 12..23)
+    float acc[16];
     {
-      const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-      float m1[32];
-      umma::tmem_ld_32x32(lane_base, acc);
-      umma::tmem_ld_32x32(lane_base + 32, m1);
+      const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 12u * part;
+      float m1[16], m2[16];
+      umma::tmem_ld_32x16(lane_base, acc);
+      umma::tmem_ld_32x16(lane_base + 32, m1);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) acc[c] += m1[c];
-      float m2[32];
-      umma::tmem_ld_32x32(lane_base + 64, m2);
-      umma::tmem_ld_32x32(lane_base + 96, m1);
+      for (int c = 0; c < 16; ++c) acc[c] += m1[c];
+      umma::tmem_ld_32x16(lane_base + 64, m2);
+      umma::tmem_ld_32x16(lane_base + 96, m1);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) acc[c] += m2[c] + m1[c];
-      umma::tmem_ld_32x32(lane_base + 128, m1);
+      for (int c = 0; c < 16; ++c) acc[c] += m2[c] + m1[c];
+      umma::tmem_ld_32x16(lane_base + 128, m1);  // cross terms
 #pragma unroll
-      for (int c = 0; c < 32; ++c) acc[c] += m1[c];
+      for (int c = 0; c < 16; ++c) acc[c] += m1[c];
       umma::fence_before_thread_sync();
     }
-    const int t = t0 + warp * 32 + lane;
+    const int t = t0 + (warp & 3) * 32 + lane;
     if (t < p.slots) {
       const RowDest d = row_dest(p.out, b, t, frames_b, sections_b);
-      const float2* st0 = nullptr;
-      if (p.out.stats) st0 = p.out.stats + (long long)b * p.out.stats_clip_stride + p.out.stats_off;
+      const float2* st = nullptr;
       const int col0 = kFCqt - kBinsPerOctave * (oct + 1);
+      if (p.out.stats)
+        st = p.out.stats + (long long)b * p.out.stats_clip_stride + p.out.stats_off + part * p.out.f_stats + col0;
+      const long long plane_off = part ? d.plane : 0;
 #pragma unroll
       for (int j = 0; j < kBinsPerOctave; ++j) {
-        const float s = __ldg(p.scale + oct * kBinsPerOctave + j);
-        float re = acc[j] * s, im = acc[kBinsPerOctave + j] * s;
-        if (st0) {
-          const float2 m0 = __ldg(st0 + col0 + j), m1s = __ldg(st0 + p.out.f_stats + col0 + j);
-          re = (re - m0.x) * m0.y;
-          im = (im - m1s.x) * m1s.y;
+        float val = acc[j] * __ldg(p.scale + oct * kBinsPerOctave + j);
+        if (st) {
+          const float2 ms = __ldg(st + j);
+          val = (val - ms.x) * ms.y;
         }
-        for (int r = 0; r < d.n; ++r) {
-          d.row[r][col0 + j] = d.live[r] ? re : 0.f;
-          d.row[r][d.plane + col0 + j] = d.live[r] ? im : 0.f;
-        }
+        if (d.n > 0) d.row[0][plane_off + col0 + j] = d.live[0] ? val : 0.f;
+        if (d.n > 1) d.row[1][plane_off + col0 + j] = d.live[1] ? val : 0.f;
       }
     }
     // every thread's TMEM reads are complete (wait::ld) before the next tile's first MMA can be issued:

@@ -139,7 +139,7 @@ constexpr int kRT = 135;                      // rows per chunk column (odd mult
 constexpr int kKSteps = kShifts * kCh / 2;    // 56 MMAs of K = 8 per operand pair
 constexpr int kStripRows = 256;
 constexpr int kStripRow0 = 4 * (kKSteps - 1); // 220: strip row of (u = 0, ks = 0)
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
 constexpr int kAFloats = kCh * kRT * 4;
 constexpr int kTFloats = 2 * kStripRows * 4;
 constexpr size_t kSmem = sizeof(float) * (2 * kAFloats + 2 * kTFloats) + 64;
@@ -163,15 +163,18 @@ struct DecimateTcParams {
   const float* strip_lo;
 };
 
-// what one tile reads / writes
+// what one tile reads / writes, and this thread's share of the staging: chunk i is read at s0 + i * 1024 samples
+// and stored at slot0 + 16 i (u = tid + 256 i -> row R = (tid >> 4) + 16 i, chunk e = tid & 15)
 struct DecTile {
   const float* x;
   float* y;
   int len_in, len_out, row0;
-  bool live;  // false: the tile lies past the clip's end (ragged batch), nothing to do
+  int s0, slot0, n;
+  bool live;      // false: the tile lies past the clip's end (ragged batch), nothing to do
+  bool interior;  // whole segment inside [0, len_in): no bounds checks
 };
 
-__device__ __forceinline__ DecTile decode_dec_tile(const DecimateTcParams& p, int tile) {
+__device__ __forceinline__ DecTile decode_dec_tile(const DecimateTcParams& p, int tile, int tid) {
   using namespace tc;
   DecTile t;
   const int b = tile / p.tiles_per_clip;
@@ -182,29 +185,25 @@ __device__ __forceinline__ DecTile decode_dec_tile(const DecimateTcParams& p, in
   t.live = t.row0 * kNB < t.len_out;
   t.x = p.in + (long long)b * p.in_stride;
   t.y = p.out + (long long)b * p.out_stride;
+  const int s_base = kRowHop * t.row0 - kDecHalf;
+  t.s0 = s_base + kRowHop * (tid >> 4) + 4 * (tid & 15);
+  t.slot0 = (tid & 15) * kRT + (tid >> 4);
+  t.n = tid < kRowsUsed * kCh ? (kRowsUsed * kCh - tid + kThreads - 1) / kThreads : 0;
+  t.interior = s_base >= 0 && s_base + kRowsUsed * kRowHop <= t.len_in && p.vec_ok;
   return t;
 }
 
-// issue the global loads of a tile's signal segment: chunk u -> row R = u / 16, chunk e = u % 16
-__device__ __forceinline__ void prefetch_dec_tile(const DecTile& t, bool vec_ok, int tid, float4 (&v)[tc::kLoadIters]) {
+__device__ __forceinline__ void prefetch_dec_tile(const DecTile& t, bool vec_ok, float4 (&v)[tc::kLoadIters]) {
   using namespace tc;
-  const int s_base = kRowHop * t.row0 - kDecHalf;
+  if (!t.live) return;
+  if (t.interior) {
 #pragma unroll
-  for (int i = 0; i < kLoadIters; ++i) {
-    const int u = tid + i * kThreads;
-    const int R = u >> 4, e = u & 15;
-    const int s = s_base + kRowHop * R + 4 * e;
-    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (u < kRowsUsed * kCh && t.live) {
-      if (s >= 0 && s + 3 < t.len_in && vec_ok) {
-        v[i] = __ldg(reinterpret_cast<const float4*>(t.x + s));
-      } else {
-        if (s >= 0 && s < t.len_in) v[i].x = __ldg(t.x + s);
-        if (s + 1 >= 0 && s + 1 < t.len_in) v[i].y = __ldg(t.x + s + 1);
-        if (s + 2 >= 0 && s + 2 < t.len_in) v[i].z = __ldg(t.x + s + 2);
-        if (s + 3 >= 0 && s + 3 < t.len_in) v[i].w = __ldg(t.x + s + 3);
-      }
-    }
+    for (int i = 0; i < kLoadIters; ++i)
+      if (i < t.n) v[i] = __ldg(reinterpret_cast<const float4*>(t.x + t.s0 + i * (16 * kRowHop)));
+  } else {
+#pragma unroll
+    for (int i = 0; i < kLoadIters; ++i)
+      if (i < t.n) v[i] = umma::load4_zero_ext(t.x, t.s0 + i * (16 * kRowHop), t.len_in, vec_ok);
   }
 }
 
@@ -235,29 +234,23 @@ __global__ void __launch_bounds__(tc::kThreads, 2) decimate2_tc_kernel(const Dec
   const uint32_t t_hi_addr = umma::smem_u32(t_hi), t_lo_addr = umma::smem_u32(t_lo);
 
   uint32_t phase = 0;
-  const int total = p.tiles_per_clip * p.batch;
+  const int total = p.tiles_per_clip * p.batch;  // gridDim.x <= total
   // software pipeline: the next tile's global loads are in flight while the tensor core works on this one
   float4 v[kLoadIters];
-  DecTile cur = decode_dec_tile(p, min((int)blockIdx.x, total - 1));
-  prefetch_dec_tile(cur, p.vec_ok, tid, v);
+  DecTile cur = decode_dec_tile(p, blockIdx.x, tid);
+  prefetch_dec_tile(cur, p.vec_ok, v);
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
     const DecTile t = cur;
     // ---- split into TF32 hi / lo and store in chunk-column order: slot [e][R]
+    if (t.live) {
 #pragma unroll
-    for (int i = 0; i < kLoadIters; ++i) {
-      const int u = tid + i * kThreads;
-      if (u < kRowsUsed * kCh) {
-        const int R = u >> 4, e = u & 15;
-        float4 h, l;
-        h.x = __uint_as_float(umma::tf32_trunc_bits(__float_as_uint(v[i].x)));
-        h.y = __uint_as_float(umma::tf32_trunc_bits(__float_as_uint(v[i].y)));
-        h.z = __uint_as_float(umma::tf32_trunc_bits(__float_as_uint(v[i].z)));
-        h.w = __uint_as_float(umma::tf32_trunc_bits(__float_as_uint(v[i].w)));
-        l.x = v[i].x - h.x, l.y = v[i].y - h.y, l.z = v[i].z - h.z, l.w = v[i].w - h.w;  // exact
-        const int slot = e * kRT + R;
-        reinterpret_cast<float4*>(a_hi)[slot] = h;
-        reinterpret_cast<float4*>(a_lo)[slot] = l;
-      }
+      for (int i = 0; i < kLoadIters; ++i)
+        if (i < t.n) {
+          float4 h, l;
+          umma::split_tf32(v[i], h, l);
+          reinterpret_cast<float4*>(a_hi)[t.slot0 + 16 * i] = h;
+          reinterpret_cast<float4*>(a_lo)[t.slot0 + 16 * i] = l;
+        }
     }
     umma::fence_proxy_async_smem();
     umma::fence_before_thread_sync();
@@ -288,8 +281,8 @@ __global__ void __launch_bounds__(tc::kThreads, 2) decimate2_tc_kernel(const Dec
     __syncwarp();
 
     if (tile + (int)gridDim.x < total) {
-      cur = decode_dec_tile(p, tile + gridDim.x);
-      prefetch_dec_tile(cur, p.vec_ok, tid, v);
+      cur = decode_dec_tile(p, tile + gridDim.x, tid);
+      prefetch_dec_tile(cur, p.vec_ok, v);
     }
     if (!t.live) continue;  // CTA-uniform
 
@@ -297,34 +290,35 @@ __global__ void __launch_bounds__(tc::kThreads, 2) decimate2_tc_kernel(const Dec
     phase ^= 1;
     umma::fence_after_thread_sync();
 
-    // ---- epilogue: thread (warp, lane) owns GEMM row 32 warp + lane = 32 consecutive outputs
-    float acc[32];
+    // ---- epilogue: GEMM row 32 (warp & 3) + lane = 32 consecutive outputs; warps 0-3 take columns 0..15,
+    //      warps 4-7 columns 16..31
+    const int part = warp >> 2;
+    float acc[16];
     {
-      const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-      float m1[32];
-      umma::tmem_ld_32x32(lane_base, acc);
-      umma::tmem_ld_32x32(lane_base + 32, m1);
+      const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 16u * part;
+      float m1[16], m2[16];
+      umma::tmem_ld_32x16(lane_base, acc);
+      umma::tmem_ld_32x16(lane_base + 32, m1);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) acc[c] += m1[c];
-      float m2[32];
-      umma::tmem_ld_32x32(lane_base + 64, m2);
-      umma::tmem_ld_32x32(lane_base + 96, m1);
+      for (int c = 0; c < 16; ++c) acc[c] += m1[c];
+      umma::tmem_ld_32x16(lane_base + 64, m2);
+      umma::tmem_ld_32x16(lane_base + 96, m1);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) acc[c] += m2[c] + m1[c];
-      umma::tmem_ld_32x32(lane_base + 128, m1);  // cross terms
+      for (int c = 0; c < 16; ++c) acc[c] += m2[c] + m1[c];
+      umma::tmem_ld_32x16(lane_base + 128, m1);  // cross terms
 #pragma unroll
-      for (int c = 0; c < 32; ++c) acc[c] += m1[c];
+      for (int c = 0; c < 16; ++c) acc[c] += m1[c];
     }
     umma::fence_before_thread_sync();
-    const int j0 = (t.row0 + warp * 32 + lane) * kNB;
+    const int j0 = (t.row0 + (warp & 3) * 32 + lane) * kNB + 16 * part;
     float* __restrict__ y = t.y + j0;
-    if (j0 + kNB <= t.len_out) {
+    if (j0 + 16 <= t.len_out) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
+      for (int q = 0; q < 4; ++q)
         reinterpret_cast<float4*>(y)[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
     } else {
 #pragma unroll
-      for (int c = 0; c < kNB; ++c)
+      for (int c = 0; c < 16; ++c)
         if (j0 + c < t.len_out) y[c] = acc[c];
     }
   }

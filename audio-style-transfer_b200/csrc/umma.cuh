@@ -112,5 +112,40 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// split 4 floats into their TF32 truncation (hi) and the exact residual (lo)
+__device__ __forceinline__ void split_tf32(const float4& v, float4& h, float4& l) {
+  h.x = __uint_as_float(tf32_trunc_bits(__float_as_uint(v.x)));
+  h.y = __uint_as_float(tf32_trunc_bits(__float_as_uint(v.y)));
+  h.z = __uint_as_float(tf32_trunc_bits(__float_as_uint(v.z)));
+  h.w = __uint_as_float(tf32_trunc_bits(__float_as_uint(v.w)));
+  l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
+}
+
+// x[s .. s+3] with zeros outside [0, len)
+__device__ __forceinline__ float4 load4_zero_ext(const float* __restrict__ x, int s, int len, bool vec_ok) {
+  if (s >= 0 && s + 3 < len && vec_ok) return __ldg(reinterpret_cast<const float4*>(x + s));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s >= 0 && s < len) v.x = __ldg(x + s);
+  if (s + 1 >= 0 && s + 1 < len) v.y = __ldg(x + s + 1);
+  if (s + 2 >= 0 && s + 2 < len) v.z = __ldg(x + s + 2);
+  if (s + 3 >= 0 && s + 3 < len) v.w = __ldg(x + s + 3);
+  return v;
+}
+
 }  // namespace umma
 }  // namespace ast

