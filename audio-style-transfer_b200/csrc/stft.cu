@@ -106,7 +106,7 @@ __device__ __forceinline__ void frame_rows(const OutSpec& o, int b, int t, int f
   }
 }
 
-__global__ void __launch_bounds__(kStftThreads, 2) stft_kernel(const StftParams p) {
+__global__ void __launch_bounds__(kStftThreads, 3) stft_kernel(const StftParams p) {
   extern __shared__ __align__(16) float2 smem[];
   float2* t1 = smem;
   float2* t2 = smem + kTw1Size;

@@ -137,7 +137,8 @@ class FrontEnd:
     # ------------------------------------------------------------------ a1-a6 fused
     def features(self, wave: torch.Tensor, lengths: Optional[torch.Tensor] = None, mean: Optional[torch.Tensor] = None,
                  std: Optional[torch.Tensor] = None, eps: float = 1e-8, layout: str = "sections",
-                 out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                 out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None
+                 ) -> Tuple[torch.Tensor, torch.Tensor]:
         """STFT + CQT + normalise + concat (+ section cut) for a batch (``dataloader.py:100-112``).
 
         ``mean`` / ``std``: ``(2, 597)`` shared, ``(B, 2, 597)`` per clip, or ``None`` (raw features).
@@ -174,12 +175,68 @@ class FrontEnd:
             raise ValueError(f"out must be a contiguous float32 {shape} tensor on {self.device}")
         counts = torch.empty((B,), dtype=torch.int32, device=self.device)
         nbytes = self.lib.ast_workspace_bytes(self._plan, B, L)
-        ws = self._workspace(nbytes)
+        if workspace is None:
+            ws = self._workspace(nbytes)
+        else:  # caller-owned scratch (needed when several streams are in flight at once)
+            ws = workspace
+            if ws.numel() * ws.element_size() < nbytes or ws.device != self.device:
+                raise ValueError(f"workspace needs {nbytes} bytes on {self.device}")
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ast_features_forward(
                 self._plan, _ptr(wave), _ptr(lengths), B, L, self._row_stride(wave), _ptr(mean), _ptr(std), per_clip,
                 float(eps), _ptr(ws), nbytes, _ptr(out), dim1, lay, _ptr(counts), _stream_ptr(self.device)))
         return out, counts
+
+    def workspace_bytes(self, batch: int, n_samples: int) -> int:
+        return int(self.lib.ast_workspace_bytes(self._plan, int(batch), int(n_samples)))
+
+    def features_host(self, host_wave: torch.Tensor, host_out: torch.Tensor, mean: Optional[torch.Tensor] = None,
+                      std: Optional[torch.Tensor] = None, eps: float = 1e-8, chunk: int = 16, n_streams: int = 3) -> torch.Tensor:
+        """The host-buffer form of :meth:`features` (sections layout): ``host_wave (B, L)`` float32 in (pinned) host
+        memory -> ``host_out (B, S, 2, 287, 597)`` float32 in (pinned) host memory.  Clips are cut into chunks and
+        H2D copy, kernels and D2H copy of successive chunks overlap on ``n_streams`` CUDA streams (PCIe is full
+        duplex), each with its own device buffers and scratch.  Returns ``host_out`` after everything has landed."""
+        if host_wave.ndim != 2 or host_wave.dtype != torch.float32 or host_wave.is_cuda:
+            raise ValueError("host_wave must be a (B, L) float32 host tensor")
+        B, L = host_wave.shape
+        S = num_sections(num_frames(L), self.window_size, self.overlap_frames)
+        shape = (B, S, 2, self.window_size, F_TOTAL)
+        if tuple(host_out.shape) != shape or host_out.dtype != torch.float32 or host_out.is_cuda or not host_out.is_contiguous():
+            raise ValueError(f"host_out must be a contiguous float32 host tensor of shape {shape}")
+        chunk = max(1, min(int(chunk), B))
+        if mean is not None:
+            mean = mean.to(device=self.device, dtype=torch.float32).contiguous()
+            std = std.to(device=self.device, dtype=torch.float32).contiguous()
+        key = (chunk, L, S, int(n_streams))
+        pipe = getattr(self, "_pipe", None)
+        if pipe is None or pipe["key"] != key:
+            with torch.cuda.device(self.device):
+                pipe = {"key": key, "slots": [{
+                    "stream": torch.cuda.Stream(device=self.device),
+                    "x": torch.empty((chunk, L + (L % 2)), dtype=torch.float32, device=self.device),
+                    "y": torch.empty((chunk,) + shape[1:], dtype=torch.float32, device=self.device),
+                    "ws": torch.empty(self.workspace_bytes(chunk, L), dtype=torch.uint8, device=self.device),
+                } for _ in range(int(n_streams))]}
+            self._pipe = pipe
+        cur = torch.cuda.current_stream(self.device)
+        for slot in pipe["slots"]:
+            slot["stream"].wait_stream(cur)
+        for i, lo in enumerate(range(0, B, chunk)):
+            hi = min(lo + chunk, B)
+            n = hi - lo
+            slot = pipe["slots"][i % len(pipe["slots"])]
+            with torch.cuda.stream(slot["stream"]):
+                x = slot["x"][:n, :L]
+                x.copy_(host_wave[lo:hi], non_blocking=True)
+                m, sd = mean, std
+                if mean is not None and mean.ndim == 3:
+                    m, sd = mean[lo:hi], std[lo:hi]
+                y, _ = self.features(x, mean=m, std=sd, eps=eps, layout="sections", out=slot["y"][:n], workspace=slot["ws"])
+                host_out[lo:hi].copy_(y, non_blocking=True)
+        for slot in pipe["slots"]:
+            cur.wait_stream(slot["stream"])
+        cur.synchronize()
+        return host_out
 
     # ------------------------------------------------------------------ a7-a9 fused
     def istft(self, spec: torch.Tensor, layout: str = "flat", overlap: Optional[int] = None,

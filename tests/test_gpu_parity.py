@@ -406,3 +406,19 @@ def test_full_batch_properties(fe, piano_stats):
     err = (y[:, :n] - wave[:, :n]).double().pow(2).sum(1)
     sig = wave[:, :n].double().pow(2).sum(1)
     assert float((10 * torch.log10(sig / err)).min()) >= 120.0
+
+
+def test_features_host_pipeline_equals_device_call(fe, piano_stats):
+    """The host-buffer API (chunked H2D / kernels / D2H over several streams) returns exactly what the
+    device-resident call returns, for chunk sizes that do and do not divide the batch."""
+    mean, std = piano_stats
+    wave = torch.from_numpy(synth.batch(7, 40000))
+    ref, _ = fe.features(wave.cuda(), mean=cuda(mean), std=cuda(std))
+    for chunk, pinned in ((3, True), (16, False), (2, True)):
+        host_in = wave.pin_memory() if pinned else wave
+        host_out = torch.empty(tuple(ref.shape), dtype=torch.float32)
+        host_out = host_out.pin_memory() if pinned else host_out
+        got = fe.features_host(host_in, host_out, mean=cuda(mean), std=cuda(std), chunk=chunk)
+        assert got is host_out and torch.equal(host_out, ref.cpu()), chunk
+    with pytest.raises(ValueError):
+        fe.features_host(wave, torch.empty(1, 2, 3))
