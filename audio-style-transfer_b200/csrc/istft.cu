@@ -15,13 +15,13 @@
 // contribution to output position (segment g, offset q) is therefore produced by the SAME thread, so the
 // overlap-add runs in registers: no atomics, no shared-memory frame store, deterministic order
 // (frames ascending, like torch's fold).  A run of R segments needs 4 halo frames.
-// Shared memory per CTA: 10 KB twiddle tables + 16.1 KB exchange buffers.
+// Shared memory per CTA: 16.1 KB exchange buffers (twiddles come from global memory through L1): 12 CTAs / SM.
 #include "common.cuh"
 
 namespace ast {
 
 constexpr int kIstftThreads = kFftThreads;  // 64
-constexpr size_t kIstftSmem = sizeof(float2) * (kTw1Size + kTw2Size + kBuf1Size + kBuf2Size);
+constexpr size_t kIstftSmem = sizeof(float2) * (kBuf1Size + kBuf2Size);  // twiddle tables are read through L1
 
 struct IstftParams {
   const float* spec;
@@ -123,15 +123,13 @@ __device__ __forceinline__ void emit_segments(const IstftParams& p, const OlaEmi
   }
 }
 
-__global__ void __launch_bounds__(kIstftThreads, 8) istft_kernel(const IstftParams p) {
+__global__ void __launch_bounds__(kIstftThreads, 12) istft_kernel(const IstftParams p) {
   extern __shared__ __align__(16) float2 smem[];
-  float2* t1 = smem;
-  float2* t2 = smem + kTw1Size;
-  float2* buf1 = smem + kTw1Size + kTw2Size;
+  const float2* __restrict__ t1 = p.t1;  // 10 KB of twiddles stay L1-resident; shared memory is kept for the
+  const float2* __restrict__ t2 = p.t2;  // exchange buffers so that 12 CTAs fit on an SM
+  float2* buf1 = smem;
   float2* buf2 = buf1 + kBuf1Size;
   const int tid = threadIdx.x;
-  for (int i = tid; i < kTw1Size; i += kIstftThreads) t1[i] = p.t1[i];
-  for (int i = tid; i < kTw2Size; i += kIstftThreads) t2[i] = p.t2[i];
 
   const int b = blockIdx.y;
   const float* __restrict__ clip = p.spec + (long long)b * p.clip_stride;
@@ -192,7 +190,7 @@ __global__ void __launch_bounds__(kIstftThreads, 8) istft_kernel(const IstftPara
   emit_segments(p, ola, wsq, renv, qs, y, t_next, g0, g1);
 }
 
-static int g_istft_ctas_per_sm = 8;
+static int g_istft_ctas_per_sm = 12;
 
 int istft_init() {
   AST_CUDA_TRY(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIstftSmem));
