@@ -52,7 +52,9 @@ constexpr int kMainAcc = 4;
 constexpr int kSetCols = kMainAcc * 2 * kN;               // 256 TMEM columns per accumulator set
 constexpr int kTmemCols = 512;
 constexpr int kStage = kM * kPassChunks / kProducers;     // 8 chunks per producer thread per pass at most
-constexpr size_t kSmem = sizeof(float) * (2 * kStageFloats + kBFloats) + 128;
+constexpr int kEpiStride = 25;            // floats per staged row (24 values + 1: conflict-free row-per-lane writes)
+constexpr int kEpiFloats = 4 * 32 * kEpiStride;  // one [32 rows][25] transpose buffer per epilogue warp
+constexpr size_t kSmem = sizeof(float) * (2 * kStageFloats + kBFloats + kEpiFloats) + 128;
 }  // namespace cqt_tc
 
 struct CqtTcParams {
@@ -172,7 +174,8 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* a_stage = reinterpret_cast<float*>(smem_raw);            // [2 stages][hi | lo]
   float* b_img = a_stage + 2 * kStageFloats;                      // 64 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_img + kBFloats);
+  float* epi_buf = b_img + kBFloats;                              // [4 warps][32][25] epilogue transpose
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + kEpiFloats);
   uint64_t* full = bars;            // [2] producers -> MMA   (8 arrivals: one per producer warp)
   uint64_t* empty = bars + 2;       // [2] MMA -> producers   (tcgen05.commit)
   uint64_t* acc_full = bars + 4;    // [2] MMA -> epilogue    (tcgen05.commit)
@@ -289,7 +292,14 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
     }
   } else {
     // ================================================================= epilogue (warps 8-11)
+    // TMEM holds one frame per lane; written that way every store instruction would touch 32 output rows
+    // (32 L1 wavefronts for 128 B).  The 32 x 24 block is therefore transposed through shared memory and
+    // stored with consecutive lanes on consecutive columns of a row (12-float runs, ~3 rows per instruction).
     const int quad = warp - kEpilogueWarp0;  // == warp % 4: the TMEM lane quadrant this warp may read
+    float* stg = epi_buf + quad * 32 * kEpiStride;
+    const long long clip_floats = p.out.layout == AST_LAYOUT_FLAT ? 2LL * p.out.dim1 * p.out.f_row
+                                                                  : 2LL * p.out.dim1 * p.out.window * p.out.f_row;
+    const long long plane = (long long)(p.out.layout == AST_LAYOUT_FLAT ? p.out.dim1 : p.out.window) * p.out.f_row;
     int n_tile = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++n_tile) {
       const int q = n_tile & 1;
@@ -298,6 +308,29 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
       const long long len0 = p.lengths ? p.lengths[b] : p.max_samples;
       const int frames_b = num_frames(len0);
       const int sections_b = p.out.layout == AST_LAYOUT_SECTIONS ? num_sections(frames_b, p.out.window, p.overlap) : 0;
+      const int col0 = kFCqt - kBinsPerOctave * (oct + 1);
+      // lane c < 24 keeps the constants of output column c (12 re then 12 im): scale, mean, 1 / (std + eps)
+      float sc_l = 0.f, mean_l = 0.f, rstd_l = 1.f;
+      if (lane < kCqtCols) {
+        const int j = lane < kBinsPerOctave ? lane : lane - kBinsPerOctave;
+        sc_l = __ldg(p.scale + oct * kBinsPerOctave + j);
+        if (p.out.stats) {
+          const float2 m = __ldg(p.out.stats + (long long)b * p.out.stats_clip_stride + p.out.stats_off + col0 + j +
+                                 (lane < kBinsPerOctave ? 0 : p.out.f_stats));
+          mean_l = m.x, rstd_l = m.y;
+        }
+      }
+      // destination rows of this lane's frame, as offsets from the clip's first output float
+      float* const clip_out = p.out.out + (long long)b * clip_floats;
+      const int t = t0 + quad * 32 + lane;
+      long long off0 = 0, off1 = 0;
+      int flags = 0;  // bit 0 / 1: row 0 / 1 live (data, else zeros); bit 2 / 3: row 0 / 1 present
+      if (t < p.slots) {
+        const RowDest d = row_dest(p.out, b, t, frames_b, sections_b);
+        if (d.n > 0) off0 = d.row[0] - clip_out + col0, flags |= 4 | (d.live[0] ? 1 : 0);
+        if (d.n > 1) off1 = d.row[1] - clip_out + col0, flags |= 8 | (d.live[1] ? 2 : 0);
+      }
+
       umma::mbar_wait(acc_full + q, (n_tile >> 1) & 1);
       umma::fence_after_thread_sync();
       float acc[32], tmp[32];
@@ -326,31 +359,35 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(acc_empty + q);  // this warp's quadrant of the set is drained
 
-      const int t = t0 + quad * 32 + lane;
-      if (t < p.slots) {
-        const RowDest d = row_dest(p.out, b, t, frames_b, sections_b);
-        const int col0 = kFCqt - kBinsPerOctave * (oct + 1);
-        const float2* st = nullptr;
-        if (p.out.stats) st = p.out.stats + (long long)b * p.out.stats_clip_stride + p.out.stats_off + col0;
+      // scale + normalise (column constants broadcast from their lane), row-per-lane into the staging buffer
 #pragma unroll
-        for (int j = 0; j < kBinsPerOctave; ++j) {
-          const float sc = __ldg(p.scale + oct * kBinsPerOctave + j);
-          float re = acc[j] * sc, im = acc[kBinsPerOctave + j] * sc;
-          if (st) {
-            const float2 m0 = __ldg(st + j), m1 = __ldg(st + p.out.f_stats + j);
-            re = (re - m0.x) * m0.y;
-            im = (im - m1.x) * m1.y;
-          }
-          if (d.n > 0) {
-            d.row[0][col0 + j] = d.live[0] ? re : 0.f;
-            d.row[0][d.plane + col0 + j] = d.live[0] ? im : 0.f;
-          }
-          if (d.n > 1) {
-            d.row[1][col0 + j] = d.live[1] ? re : 0.f;
-            d.row[1][d.plane + col0 + j] = d.live[1] ? im : 0.f;
-          }
+      for (int c = 0; c < kCqtCols; ++c) {
+        const float sc = __shfl_sync(0xffffffffu, sc_l, c);
+        const float mu = __shfl_sync(0xffffffffu, mean_l, c);
+        const float rs = __shfl_sync(0xffffffffu, rstd_l, c);
+        float v = acc[c] * sc;
+        if (p.out.stats) v = (v - mu) * rs;
+        stg[lane * kEpiStride + c] = v;
+      }
+      __syncwarp();
+      // 32 rows x 12 columns per plane = 12 store rounds; lane l of round i owns element 32 i + l
+#pragma unroll
+      for (int i = 0; i < kBinsPerOctave; ++i) {
+        const int idx = lane + 32 * i;
+        const int r = idx / kBinsPerOctave, j = idx - r * kBinsPerOctave;
+        const float re = stg[r * kEpiStride + j], im = stg[r * kEpiStride + kBinsPerOctave + j];
+        const long long o0 = __shfl_sync(0xffffffffu, off0, r), o1 = __shfl_sync(0xffffffffu, off1, r);
+        const int fl = __shfl_sync(0xffffffffu, flags, r);
+        if (fl & 4) {
+          clip_out[o0 + j] = (fl & 1) ? re : 0.f;
+          clip_out[o0 + plane + j] = (fl & 1) ? im : 0.f;
+        }
+        if (fl & 8) {
+          clip_out[o1 + j] = (fl & 2) ? re : 0.f;
+          clip_out[o1 + plane + j] = (fl & 2) ? im : 0.f;
         }
       }
+      __syncwarp();  // the staging buffer is rewritten by the next tile
     }
   }
   umma::fence_before_thread_sync();
