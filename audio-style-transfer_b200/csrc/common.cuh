@@ -174,7 +174,11 @@ int launch_cqt_tc(const ast_plan* plan, const float* wave, const int32_t* length
 void set_tc_cqt(int on);
 void set_overlap_streams(int on);
 bool use_tc_cqt();
-void host_decimator_strip(const double* taps_scaled, float* strip_hi, float* strip_lo);  // 2 x 2048 floats
+int decimator_strip_floats();
+void host_decimator_strip(const double* taps_scaled, float* strip_hi, float* strip_lo);  // decimator_strip_floats() each
+int launch_decimate2_tc(const ast_plan* plan, const float* in, long long in_stride, float* out, long long out_stride,
+                        const int32_t* lengths, long long max_samples, int in_octave, int batch, bool vec_ok,
+                        cudaStream_t st);
 void set_tc_decimator(int on);
 int istft_init();  // into __constant__ memory of decimate.cu
 

@@ -1,0 +1,377 @@
+// decimate_tc.cu - K2 on the tensor cores: one 2:1 stage of librosa.cqt's decimation cascade
+// (audio.resample(y, orig_sr=2, target_sr=1, res_type="soxr_hq", scale=True), reached through
+// utilityFunctions.py:52) as a block-Toeplitz GEMM at the full tcgen05 rate.
+//
+//   y[j] = sum_{k=0}^{384} g[k] x[2 j + k - 192]      (zero extension, len_out = ceil(len_in / 2))
+//
+// Measured on B200 (scratch/mma_bench2.cu): an M128 K8 kind::tf32 MMA with both operands in shared memory costs
+// max(~40, N / 2) cycles, so only N = 256 runs the tensor pipe at its peak.  The signal is therefore cut into
+// NON-overlapping rows of 128 samples (row R = x[128 R - 192 ...]) and the 511-sample window of the 64 outputs
+// y[64 R ... 64 R + 63] into D = 4 row blocks:
+//
+//   Y[R][u] = sum_{d < 4} Z[R + d][64 (3 - d) + u],      Z[rho][64 (3 - d) + u] = sum_{i < 128} X[rho][i] g[128 d + i - 2 u]
+//
+// Z = X * G is ONE GEMM with N = 256: A = X (128 rows x 128 samples, plain rows, no im2col, no shifted
+// descriptors) and, because the blocks are laid out in reverse order along N, B is a single Toeplitz strip
+// T[jj][kk] = g[kk - 2 jj]: K-step gs (8 samples) reads strip rows (60 - 4 gs) ... + 255 - just a start-address
+// shift in the no-swizzle K-major layout (rows 16 B apart).  The row shift R + d is applied in the epilogue with
+// warp shuffles; each warp owns 32 consecutive rows and emits the 29 complete ones, so the four row groups of a
+// tile overlap by three rows (116 output rows = 7424 outputs per tile).
+//
+// FP32 accuracy: x = hi + lo (hi = what the tensor core keeps of an FP32 operand: truncation to TF32, measured;
+// so the RAW samples are the hi operand, no masking needed) and
+// g = hi + lo (host, from the double taps).  The tensor core accumulates with round-toward-zero (about -1.4e-8
+// relative per accumulating MMA at full magnitude), so per tile the 32 small cross-term MMAs (lo*hi, hi*lo) are
+// issued FIRST - their truncation error scales with the still tiny accumulator - and the 16 hi*hi MMAs last.
+//
+// One persistent CTA per SM, 13 warps:
+//   warps 0-7   producers: the NEXT tile's 64 KB of samples are loaded into registers (16 x LDG.128 per thread) while
+//               the current one is stored: raw -> A_hi (two whole tiles resident), x - trunc(x) -> A_lo (2-stage
+//               ring of 32-sample slices).  (cp.async was tried first: LDGSTS with a scattered destination costs
+//               one shared-memory wavefront per thread, 8x the LDG + conflict-free STS.128 path - ncu, profiles/.)
+//   warps 8-11  epilogue : TMEM -> registers, shifted sum by shuffles, stores (two accumulators, ping-pong)
+//   warp  12    MMA issue
+#include <cstring>
+#include <type_traits>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace ast {
+
+namespace dtc {
+constexpr int kM = 128;                          // staged rows per tile (TMEM lanes)
+constexpr int kGroupValid = 29;                  // complete output rows per 32-row group (rows R, R+1, R+2, R+3 needed)
+constexpr int kGroups = 4;
+constexpr int kRowsOut = kGroups * kGroupValid;  // 116
+constexpr int kP = 64;                           // outputs per row
+constexpr int kRS = 2 * kP;                      // 128 input samples per row
+constexpr int kD = 4;                            // row blocks per window: 4 * 128 = 512 >= 2 * 63 + 385
+constexpr int kN = kD * kP;                      // 256
+constexpr int kSlices = 4;                       // 32-sample K slices per tile
+constexpr int kSliceChunks = 8;                  // 16-byte chunks per row per slice
+constexpr int kKStepsPerSlice = 4;
+constexpr int kRT = 129;                         // rows per chunk column (odd: conflict-free 16-byte stores)
+constexpr int kSliceFloats = kSliceChunks * kRT * 4;   // 4128 floats = 16 512 B
+constexpr int kTileFloats = kSlices * kSliceFloats;    // A_hi of one tile
+constexpr int kStripRows = 320;                  // 316 used: jj = -252 ... 63
+constexpr int kStripRow0 = 60;                   // strip row of (n = 0, gs = 0): jj = -192
+constexpr int kStripFloats = 2 * kStripRows * 4; // [chunk 2][row 320][4]
+constexpr int kProducers = 256;
+constexpr int kEpilogueWarp0 = 8;
+constexpr int kMmaWarp = 12;
+constexpr int kThreads = 13 * 32;
+constexpr int kTmemCols = 512;                   // two 256-column accumulators
+constexpr int kChunksPerThread = kM * kSliceChunks / kProducers;  // 4
+constexpr int kEpiStride = kP + 4;               // floats per staged output row (conflict-free 16-byte accesses)
+constexpr int kEpiFloats = 4 * 32 * kEpiStride;  // one [32 rows][68] transpose buffer per epilogue warp
+constexpr size_t kSmem = sizeof(float) * (2 * kTileFloats + 2 * kSliceFloats + 2 * kStripFloats + kEpiFloats) + 128;
+}  // namespace dtc
+
+struct DecimateTcParams {
+  const float* in;
+  long long in_stride;
+  float* out;
+  long long out_stride;
+  const int32_t* lengths;
+  long long max_samples;
+  int in_octave;
+  int batch;
+  int tiles_per_clip;
+  bool vec_ok;
+  const float* strip_hi;   // [2][320][4] smem image of the Toeplitz strip (TF32-exact values)
+  const float* strip_lo;
+};
+
+struct DtcTile {
+  const float* x;
+  float* y;
+  int len_in, len_out;
+  int row0;        // first row of the tile (rows advance by 116 per tile)
+  bool live;       // false: the tile lies past the clip's end (ragged batch)
+  bool interior;   // every staged sample lies inside [0, len_in) and 16-byte copies are legal
+};
+
+__device__ __forceinline__ DtcTile dtc_decode(const DecimateTcParams& p, int tile) {
+  using namespace dtc;
+  DtcTile t;
+  const int b = tile / p.tiles_per_clip;
+  t.row0 = (tile - b * p.tiles_per_clip) * kRowsOut;
+  const long long len0 = p.lengths ? p.lengths[b] : p.max_samples;
+  t.len_in = (int)((len0 + (1LL << p.in_octave) - 1) >> p.in_octave);
+  t.len_out = (t.len_in + 1) >> 1;
+  t.live = t.row0 * kP < t.len_out;
+  t.x = p.in + (long long)b * p.in_stride;
+  t.y = p.out + (long long)b * p.out_stride;
+  const int first = kRS * t.row0 - kDecHalf;
+  const int last = kRS * (t.row0 + kGroupValid * (kGroups - 1) + 31) - kDecHalf + kRS;  // one past the last staged sample
+  t.interior = first >= 0 && last <= t.len_in && p.vec_ok;
+  return t;
+}
+
+__device__ __forceinline__ int dtc_next_live(const DecimateTcParams& p, int tile, int total) {
+  for (tile += gridDim.x; tile < total; tile += gridDim.x)
+    if (dtc_decode(p, tile).live) return tile;
+  return -1;
+}
+
+// One 32-sample slice of a tile for this producer thread: chunk c = tid & 7 of rows (tid >> 3) + 32 i, i = 0..3
+// (row group i), read at sample 128 (row0 + 29 i + (tid >> 3)) - 192 + 32 s + 4 c.
+template <int S>
+__device__ __forceinline__ void dtc_load_slice(const DtcTile& t, int tid, bool vec_ok, float4 (&v)[16]) {
+  using namespace dtc;
+  const int a0 = kRS * (t.row0 + (tid >> 3)) - kDecHalf + 32 * S + 4 * (tid & 7);
+  if (t.interior) {
+#pragma unroll
+    for (int i = 0; i < kChunksPerThread; ++i)
+      v[4 * S + i] = __ldg(reinterpret_cast<const float4*>(t.x + a0 + kRS * kGroupValid * i));
+  } else {
+#pragma unroll
+    for (int i = 0; i < kChunksPerThread; ++i)
+      v[4 * S + i] = umma::load4_zero_ext(t.x, a0 + kRS * kGroupValid * i, t.len_in, vec_ok);
+  }
+}
+
+__global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const DecimateTcParams p) {
+  using namespace dtc;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* a_hi = reinterpret_cast<float*>(smem_raw);      // [2 tiles][4 slices][8 chunk columns][129 rows][4]
+  float* a_lo = a_hi + 2 * kTileFloats;                  // [2 stages][8][129][4]
+  float* t_hi = a_lo + 2 * kSliceFloats;
+  float* t_lo = t_hi + kStripFloats;
+  float* epi_buf = t_lo + kStripFloats;                  // [4 warps][32 rows][68] epilogue transpose
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + kEpiFloats);
+  uint64_t* l_full = bars;          // [2] producers -> MMA: slice staged (raw + lo written); 8 warp arrivals
+  uint64_t* l_empty = bars + 2;     // [2] MMA -> producers: the cross-term MMAs of the slice are done
+  uint64_t* h_empty = bars + 4;     // [2] MMA -> producers: all MMAs of the tile in this A_hi buffer are done
+  uint64_t* acc_full = bars + 6;    // [2] MMA -> epilogue
+  uint64_t* acc_empty = bars + 8;   // [2] epilogue -> MMA; 4 warp arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < kStripFloats / 4; i += kThreads) {
+    reinterpret_cast<float4*>(t_hi)[i] = __ldg(reinterpret_cast<const float4*>(p.strip_hi) + i);
+    reinterpret_cast<float4*>(t_lo)[i] = __ldg(reinterpret_cast<const float4*>(p.strip_lo) + i);
+  }
+  if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, kTmemCols);
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(l_full + i, kProducers / 32);
+      umma::mbar_init(l_empty + i, 1);
+      umma::mbar_init(h_empty + i, 1);
+      umma::mbar_init(acc_full + i, 1);
+      umma::mbar_init(acc_empty + i, 4);
+    }
+  }
+  umma::fence_proxy_async_smem();
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total = p.tiles_per_clip * p.batch;
+  int tile = blockIdx.x;
+  if (tile < total && !dtc_decode(p, tile).live) tile = dtc_next_live(p, tile, total);
+
+  if (warp < kProducers / 32) {
+    // ================================================================= producers
+    float4 v[16];  // one whole tile per CTA in registers: v[4 s + i] = slice s, row group i
+    const int slot0 = (tid & 7) * kRT + (tid >> 3);
+    DtcTile cur;
+    if (tile >= 0 && tile < total) {
+      cur = dtc_decode(p, tile);
+      dtc_load_slice<0>(cur, tid, p.vec_ok, v);
+      dtc_load_slice<1>(cur, tid, p.vec_ok, v);
+      dtc_load_slice<2>(cur, tid, p.vec_ok, v);
+      dtc_load_slice<3>(cur, tid, p.vec_ok, v);
+    }
+    for (int n = 0; tile >= 0 && tile < total; ++n) {
+      const int next = dtc_next_live(p, tile, total);
+      if (next >= 0) cur = dtc_decode(p, next);
+      // this A_hi buffer is free once the MMAs of tile n - 2 have completed
+      umma::mbar_wait(h_empty + (n & 1), ((n >> 1) & 1) ^ 1);
+      float4* hi_tile = reinterpret_cast<float4*>(a_hi + (n & 1) * kTileFloats);
+      auto stage = [&](auto s_tag) {
+        constexpr int S = decltype(s_tag)::value;
+        const int qs = 4 * n + S, st = qs & 1;
+        umma::mbar_wait(l_empty + st, ((qs >> 1) & 1) ^ 1);  // the cross MMAs that read this lo stage two slices ago are done
+        float4* hi = hi_tile + S * (kSliceFloats / 4);
+        float4* lo = reinterpret_cast<float4*>(a_lo + st * kSliceFloats);
+#pragma unroll
+        for (int i = 0; i < kChunksPerThread; ++i) {
+          float4 h, l;
+          umma::split_tf32(v[4 * S + i], h, l);
+          hi[slot0 + 32 * i] = v[4 * S + i];   // raw: the tensor core truncates to TF32 itself
+          lo[slot0 + 32 * i] = l;
+        }
+        umma::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(l_full + st);
+        if (next >= 0) dtc_load_slice<S>(cur, tid, p.vec_ok, v);  // refill the freed registers with the next tile
+      };
+      stage(std::integral_constant<int, 0>{});
+      stage(std::integral_constant<int, 1>{});
+      stage(std::integral_constant<int, 2>{});
+      stage(std::integral_constant<int, 3>{});
+      tile = next;
+    }
+  } else if (warp == kMmaWarp) {
+    // ================================================================= MMA issue
+    const uint32_t idesc = umma::instr_desc_tf32(kM, kN);
+    const uint64_t db_hi0 = umma::smem_desc(umma::smem_u32(t_hi), kStripRows * 16, 128) + (uint64_t)kStripRow0;
+    const uint64_t db_lo0 = umma::smem_desc(umma::smem_u32(t_lo), kStripRows * 16, 128) + (uint64_t)kStripRow0;
+    for (int n = 0; tile >= 0 && tile < total; ++n, tile = dtc_next_live(p, tile, total)) {
+      const int q = n & 1;
+      const uint32_t acc = tmem_base + (uint32_t)(q * kN);
+      const uint32_t hi_addr = umma::smem_u32(a_hi + q * kTileFloats);
+      umma::mbar_wait(acc_empty + q, ((n >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+      umma::fence_after_thread_sync();
+      // cross terms first (see the accuracy note in the header)
+      for (int s = 0; s < kSlices; ++s) {
+        const int qs = 4 * n + s, st = qs & 1;
+        umma::mbar_wait(l_full + st, (qs >> 1) & 1);
+        umma::fence_after_thread_sync();
+        if (umma::elect_one_sync()) {
+          const uint64_t da_hi = umma::smem_desc(hi_addr + (uint32_t)(s * kSliceFloats * 4), kRT * 16, 128);
+          const uint64_t da_lo = umma::smem_desc(umma::smem_u32(a_lo + st * kSliceFloats), kRT * 16, 128);
+#pragma unroll
+          for (int k = 0; k < kKStepsPerSlice; ++k) {
+            const uint64_t a_off = (uint64_t)(2 * k * kRT);              // start-address field is in 16-byte units
+            const uint64_t b_off = (uint64_t)(4 * (kKStepsPerSlice * s + k));  // strip row 60 - 4 gs
+            umma::mma_tf32(acc, da_lo + a_off, db_hi0 - b_off, idesc, (s | k) ? 1u : 0u);
+            umma::mma_tf32(acc, da_hi + a_off, db_lo0 - b_off, idesc, 1u);
+          }
+          umma::commit(l_empty + st);
+        }
+        __syncwarp();
+      }
+      if (umma::elect_one_sync()) {
+#pragma unroll
+        for (int gs = 0; gs < kSlices * kKStepsPerSlice; ++gs) {
+          const int s = gs >> 2, k = gs & 3;
+          const uint64_t da_hi = umma::smem_desc(hi_addr + (uint32_t)(s * kSliceFloats * 4), kRT * 16, 128);
+          umma::mma_tf32(acc, da_hi + (uint64_t)(2 * k * kRT), db_hi0 - (uint64_t)(4 * gs), idesc, 1u);
+        }
+        umma::commit(h_empty + q);    // this A_hi buffer may be refilled
+        umma::commit(acc_full + q);   // ... and the accumulator is complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================================================= epilogue (warps 8-11)
+    const int quad = warp - kEpilogueWarp0;  // == warp % 4: the TMEM lane quadrant this warp may read
+    float* stg = epi_buf + quad * 32 * kEpiStride;
+    for (int n = 0; tile >= 0 && tile < total; ++n, tile = dtc_next_live(p, tile, total)) {
+      const int q = n & 1;
+      const DtcTile t = dtc_decode(p, tile);
+      umma::mbar_wait(acc_full + q, (n >> 1) & 1);
+      umma::fence_after_thread_sync();
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(q * kN);
+      // lane l of row group `quad` owns output row R = row0 + 29 quad + l (complete for l < 29)
+#pragma unroll
+      for (int cq = 0; cq < kP / 16; ++cq) {
+        float v0[16], v1[16], v2[16], v3[16];
+        umma::tmem_ld_32x16(lane_base + 3 * kP + 16 * cq, v0);   // d = 0: this row
+        umma::tmem_ld_32x16(lane_base + 2 * kP + 16 * cq, v1);   // d = 1: wanted by the row above (lane - 1)
+        umma::tmem_ld_32x16(lane_base + 1 * kP + 16 * cq, v2);
+        umma::tmem_ld_32x16(lane_base + 16 * cq, v3);
+        if (cq == kP / 16 - 1) {  // last TMEM read of the tile: hand the accumulator back
+          umma::fence_before_thread_sync();
+          __syncwarp();
+          if (lane == 0) umma::mbar_arrive(acc_empty + q);
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float s1 = __shfl_down_sync(0xffffffffu, v1[c], 1);
+          const float s2 = __shfl_down_sync(0xffffffffu, v2[c], 2);
+          const float s3 = __shfl_down_sync(0xffffffffu, v3[c], 3);
+          v0[c] = (v0[c] + s1) + (s2 + s3);
+        }
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+          *reinterpret_cast<float4*>(stg + lane * kEpiStride + 16 * cq + 4 * w) =
+              make_float4(v0[4 * w], v0[4 * w + 1], v0[4 * w + 2], v0[4 * w + 3]);
+      }
+      __syncwarp();
+      // write-out along rows: 16 lanes cover one 256-byte row, so an instruction touches 4 lines instead of 29
+      const int j_grp = (t.row0 + kGroupValid * quad) * kP;
+      for (int idx = lane; idx < kGroupValid * (kP / 4); idx += 32) {
+        const int r = idx >> 4, c4 = idx & 15;
+        const int j = j_grp + r * kP + 4 * c4;
+        const float4 val = *reinterpret_cast<const float4*>(stg + r * kEpiStride + 4 * c4);
+        if (j + 4 <= t.len_out) {
+          *reinterpret_cast<float4*>(t.y + j) = val;
+        } else {
+          if (j < t.len_out) t.y[j] = val.x;
+          if (j + 1 < t.len_out) t.y[j + 1] = val.y;
+          if (j + 2 < t.len_out) t.y[j + 2] = val.z;
+        }
+      }
+      __syncwarp();  // the staging buffer is rewritten by the next tile
+    }
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) umma::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+int decimate_init() {
+  AST_CUDA_TRY(cudaFuncSetAttribute(decimate2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dtc::kSmem));
+  return AST_OK;
+}
+
+int decimator_strip_floats() { return dtc::kStripFloats; }
+
+// host: the Toeplitz strip images T[jj][kk] = g[kk - 2 jj], jj = row - 252, as [chunk c][row][4] with kk = 4 c + e;
+// hi values are exactly representable in TF32, lo is the TF32-truncated residual of the double tap.
+void host_decimator_strip(const double* taps_scaled, float* strip_hi, float* strip_lo) {
+  using namespace dtc;
+  for (int c = 0; c < 2; ++c)
+    for (int i = 0; i < kStripRows; ++i)
+      for (int e = 0; e < 4; ++e) {
+        const int jj = i - (kStripRow0 + 3 * kP);   // row 252 <-> jj = 0
+        const int tap = 4 * c + e - 2 * jj;
+        const double g = (tap >= 0 && tap < kDecTaps) ? taps_scaled[tap] : 0.0;
+        float gf = (float)g;
+        uint32_t hb;
+        memcpy(&hb, &gf, 4);
+        hb = umma::tf32_trunc_bits(hb);
+        float hi;
+        memcpy(&hi, &hb, 4);
+        float lo = (float)(g - (double)hi);
+        uint32_t lb;
+        memcpy(&lb, &lo, 4);
+        lb = umma::tf32_trunc_bits(lb);
+        memcpy(&lo, &lb, 4);
+        strip_hi[(c * kStripRows + i) * 4 + e] = hi;
+        strip_lo[(c * kStripRows + i) * 4 + e] = lo;
+      }
+}
+
+int launch_decimate2_tc(const ast_plan* plan, const float* in, long long in_stride, float* out, long long out_stride,
+                        const int32_t* lengths, long long max_samples, int in_octave, int batch, bool vec_ok,
+                        cudaStream_t st) {
+  DecimateTcParams p;
+  p.in = in;
+  p.in_stride = in_stride;
+  p.out = out;
+  p.out_stride = out_stride;
+  p.lengths = lengths;
+  p.max_samples = max_samples;
+  p.in_octave = in_octave;
+  p.batch = batch;
+  const long long len_out = octave_len(max_samples, in_octave + 1);
+  const long long rows = (len_out + dtc::kP - 1) / dtc::kP;
+  p.tiles_per_clip = (int)((rows + dtc::kRowsOut - 1) / dtc::kRowsOut);
+  p.vec_ok = vec_ok;
+  p.strip_hi = plan->d_dec_strip_hi;
+  p.strip_lo = plan->d_dec_strip_lo;
+  long long ctas = (long long)p.tiles_per_clip * batch;
+  if (ctas > plan->sm_count) ctas = plan->sm_count;  // persistent: one CTA per SM
+  if (ctas == 0) return AST_OK;
+  ProfileSpan span("decimate2_tc_kernel", st);
+  decimate2_tc_kernel<<<(unsigned)ctas, dtc::kThreads, dtc::kSmem, st>>>(p);
+  AST_LAUNCH_CHECK("decimate2_tc_kernel");
+  return AST_OK;
+}
+
+}  // namespace ast

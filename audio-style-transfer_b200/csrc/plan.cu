@@ -330,10 +330,10 @@ int ast_plan_create(const ast_config* cfg, ast_plan** out) {
   {
     std::vector<double> taps_scaled(kDecTaps);
     for (int i = 0; i < kDecTaps; ++i) taps_scaled[i] = taps[i] * std::sqrt(2.0);
-    std::vector<float> strip_hi(2048), strip_lo(2048);
+    std::vector<float> strip_hi(decimator_strip_floats()), strip_lo(decimator_strip_floats());
     host_decimator_strip(taps_scaled.data(), strip_hi.data(), strip_lo.data());
-    AST_ALLOC_COPY(p->d_dec_strip_hi, strip_hi.data(), sizeof(float) * 2048);
-    AST_ALLOC_COPY(p->d_dec_strip_lo, strip_lo.data(), sizeof(float) * 2048);
+    AST_ALLOC_COPY(p->d_dec_strip_hi, strip_hi.data(), sizeof(float) * strip_hi.size());
+    AST_ALLOC_COPY(p->d_dec_strip_lo, strip_lo.data(), sizeof(float) * strip_lo.size());
   }
 #undef AST_ALLOC_COPY
   int rc = upload_decimator_taps(taps_f.data());
