@@ -206,7 +206,9 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
         umma::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(l_full + st);
-        if (next >= 0) dtc_load_slice<S>(cur, tid, p.vec_ok, v);  // refill the freed registers with the next tile
+        // refill the freed registers with the next tile (measured: better than loading the whole tile after the
+        // last slice, although each fence.proxy.async then also waits for the previous slice's loads)
+        if (next >= 0) dtc_load_slice<S>(cur, tid, p.vec_ok, v);
       };
       stage(std::integral_constant<int, 0>{});
       stage(std::integral_constant<int, 1>{});

@@ -131,6 +131,19 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 8 columns
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // split 4 floats into their TF32 truncation (hi) and the exact residual (lo)
 __device__ __forceinline__ void split_tf32(const float4& v, float4& h, float4& l) {
   h.x = __uint_as_float(tf32_trunc_bits(__float_as_uint(v.x)));
