@@ -90,7 +90,7 @@ struct CqtTcParams {
   const float* bmat;   // [32 ks][2 c][64 j: hi then lo][4] smem image
   const float* scale;  // [7][12]
   bool vec_ok;
-  int debug;   // diagnostic bit mask (AST_CQT_DEBUG): 1 no epilogue stores, 2 no producer loads, 4 no MMAs
+  int debug;   // diagnostic bit mask (AST_CQT_DEBUG): 1 no epilogue stores, 2 no producer loads, 4 no MMAs, 8 no L2 prefetch
   OutSpec out;
 };
 
@@ -275,6 +275,22 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
         tile += gridDim.x;
         j = 0;
         if (tile < total) decode_tile(p, tile, b, oct, t0);
+        // one thread asks L2 for the signal span of the tile after that one, so its loads find it there
+        if (tid == 0 && tile + (int)gridDim.x < total && !(p.debug & 8)) {
+          int b2, oct2, t2;
+          decode_tile(p, tile + gridDim.x, b2, oct2, t2);
+          const long long len2 = ((p.lengths ? p.lengths[b2] : p.max_samples) + (1LL << oct2) - 1) >> oct2;
+          const float* x2 = oct2 == 0 ? p.wave + (long long)b2 * p.wave_stride
+                                      : p.ws + (long long)b2 * p.ws_clip_stride + p.oct_off[oct2];
+          const int hop2 = kHop >> oct2;
+          long long lo = (long long)t2 * hop2 - kCqtNfft / 2, hi = lo + (long long)(kM - 1) * hop2 + kCqtNfft;
+          if (lo < 0) lo = 0;
+          if (hi > len2) hi = len2;
+          // align to 16 bytes inside the range
+          const uintptr_t a0 = (reinterpret_cast<uintptr_t>(x2 + lo) + 15) & ~(uintptr_t)15;
+          const uintptr_t a1 = reinterpret_cast<uintptr_t>(x2 + hi) & ~(uintptr_t)15;
+          if (a1 > a0) umma::prefetch_l2_bulk(reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0));
+        }
       }
       if (tile < total) {
         sp = plan_block(p, b, oct, t0, j, tid);

@@ -72,6 +72,11 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// fire-and-forget L2 prefetch of a contiguous global range (16-byte aligned address, size a multiple of 16)
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
+
 // one lane of a fully converged warp
 __device__ __forceinline__ bool elect_one_sync() {
   uint32_t pred;
