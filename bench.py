@@ -51,10 +51,11 @@ KERNEL_BYTES_PER_CLIP = {  # compulsory input + output bytes of each kernel as t
     "cqt_tc_kernel": sum(_OCT) * 4 + BYTES_SECTIONS_CQT,
     "istft_kernel": BYTES_ISTFT_PATH,
 }
-# dense MACs per clip the two tensor-core kernels issue (3 TF32 split terms, padded tiles included)
+# dense FLOPs per clip the two tensor-core kernels issue (TF32 split terms and padded tiles included)
+_DEC_TILES = [-(-(-(-n // 64)) // 116) for n in _OCT[1:]]               # 116 rows of 64 outputs per tile: 15, 8, 4, 2, 1, 1
 TENSOR_FLOPS_PER_CLIP = {
-    "decimate2_tc_kernel": 2.0 * 3 * 448 * sum(_OCT[1:]) / 6.0,          # per launch (average of six)
-    "cqt_tc_kernel": 2.0 * 3 * 256 * 32 * 7 * 896,                        # 7 octaves x 7 tiles x 128 frames
+    "decimate2_tc_kernel": 2.0 * 3 * 128 * 256 * 128 * sum(_DEC_TILES) / 6.0,   # M128 N256 K128 x 3 terms, per launch (average of six)
+    "cqt_tc_kernel": 2.0 * 128 * 256 * (64 + 32) * 7 * 7,                       # 49 tiles x 32 K-steps x (N64 + N32) MMAs
 }
 STATS_NPZ = os.path.join(ROOT, "tests", "golden", "train_set_stats", "stats_stft_cqt_piano.npz")
 
