@@ -68,6 +68,13 @@ SIGNATURES = {
     "ast_stats_accumulate_features": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                               c_void_p, c_size_t, c_int32, c_void_p, c_void_p, c_void_p]),
     "ast_stats_finalize": (c_int, [POINTER(c_double), c_double, POINTER(c_float), POINTER(c_float)]),
+    "ast_resample_geometry": (c_int, [c_int32, c_int32, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
+    "ast_resample_length": (c_int64, [c_int64, c_int32, c_int32]),
+    "ast_host_resample_taps": (c_int, [c_int32, c_int32, POINTER(c_float), c_int32]),
+    "ast_resampler_create": (c_int, [c_int32, c_int32, c_int32, POINTER(c_void_p)]),
+    "ast_resampler_destroy": (c_int, [c_void_p]),
+    "ast_load_audio_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p,
+                                       c_int64, c_void_p]),
     "ast_profile_enable": (c_int, [c_int32]),
     "ast_profile_collect": (c_int, [c_char_p, POINTER(c_float), POINTER(c_int32), c_int32, POINTER(c_int32)]),
 }

@@ -68,8 +68,15 @@ class FrontEnd:
             _lib.check(self.lib.ast_plan_create(ctypes.byref(cfg), ctypes.byref(plan)))
         self._plan = plan
         self._ws: Optional[torch.Tensor] = None
+        self._resamplers: dict = {}
 
     def __del__(self):
+        for r in getattr(self, "_resamplers", {}).values():
+            try:
+                self.lib.ast_resampler_destroy(r)
+            except Exception:
+                pass
+        self._resamplers = {}
         plan = getattr(self, "_plan", None)
         if plan is not None and plan.value:
             try:
@@ -107,6 +114,36 @@ class FrontEnd:
     @staticmethod
     def _row_stride(wave: torch.Tensor) -> int:
         return wave.stride(0) if wave.shape[0] > 1 else wave.shape[1]
+
+    # ------------------------------------------------------------------ 8f-1: load_audio's device part, batched
+    def load_audio(self, wave: torch.Tensor, orig_sample_rate: int, sample_rate: int = SAMPLE_RATE,
+                   cut_time_seconds: float = 10, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``load_audio`` after the file decode (``utilityFunctions.py:109-120``): pad / cut to
+        ``int(cut_time_seconds * orig_sample_rate)`` samples, ``torchaudio.functional.resample`` (defaults) to
+        ``sample_rate``, mean of the two channels of a stereo clip.  ``wave`` is ``(B, C, L)`` (or ``(C, L)``),
+        C in {1, 2}; ``lengths`` optionally gives the valid samples of each clip.  Returns ``(B, L')`` float32."""
+        squeeze = wave.ndim == 2
+        if squeeze:
+            wave = wave.unsqueeze(0)
+        if wave.ndim != 3:
+            raise ValueError(f"wave must be (B, C, L) or (C, L), got {tuple(wave.shape)}")
+        wave = wave.to(device=self.device, dtype=torch.float32).contiguous()
+        B, C, L = wave.shape
+        if lengths is not None:
+            lengths = lengths.to(device=self.device, dtype=torch.int32).contiguous()
+        key = (int(orig_sample_rate), int(sample_rate))
+        r = self._resamplers.get(key)
+        if r is None:
+            r = ctypes.c_void_p()
+            _lib.check(self.lib.ast_resampler_create(key[0], key[1], self.device.index, ctypes.byref(r)))
+            self._resamplers[key] = r
+        cut = int(cut_time_seconds * orig_sample_rate)
+        n_out = int(self.lib.ast_resample_length(cut, key[0], key[1]))
+        out = torch.empty((B, n_out), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ast_load_audio_forward(r, _ptr(wave), _ptr(lengths), B, C, L, cut, _ptr(out), n_out,
+                                                       _stream_ptr(self.device)))
+        return out[0:1] if squeeze else out
 
     # ------------------------------------------------------------------ a1: get_STFT, batched
     def stft(self, wave: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -7,7 +7,8 @@ like the reference; CUDA in -> CUDA out with no host round trip).  There is no C
 without a CUDA device every function raises.
 
 Not mirrored (out of scope): ``inverse_CQT`` (dead code in the reference),
-``plot_stft`` / ``plot_cqt`` (matplotlib), ``load_audio`` (file decoding; next row §8f).
+``plot_stft`` / ``plot_cqt`` (matplotlib).  ``load_audio`` decodes the file on the host and runs everything
+after the decode (pad / cut, resample, stereo mean - SURVEY.md §8f-1) on the device.
 """
 from __future__ import annotations
 
@@ -116,3 +117,49 @@ def concat_stft_cqt(stft, cqt):
         raise ValueError(f"Channel/Time mismatch: stft {stft.shape[:2]} vs cqt {cqt.shape[:2]}")
     fe = default_frontend(_cuda_device(stft))
     return fe.concat(stft, cqt).to(_home(stft))
+
+
+def _decode_file(file_path):
+    """Host-side decode: ``torchaudio.load`` where it works (it needs ``torchcodec``), else PCM / float WAV
+    through ``scipy.io.wavfile``.  Returns ``(channels, samples)`` float32 in [-1, 1] and the file's rate."""
+    try:
+        import torchaudio
+
+        waveform, sr = torchaudio.load(file_path)
+        return waveform.to(torch.float32), int(sr)
+    except (ImportError, RuntimeError, OSError, AttributeError):
+        pass
+    from scipy.io import wavfile
+
+    sr, data = wavfile.read(file_path)
+    data = np.asarray(data)
+    if data.ndim == 1:
+        data = data[:, None]
+    if data.dtype == np.int16:
+        x = data.astype(np.float32) / 32768.0
+    elif data.dtype == np.int32:
+        x = data.astype(np.float32) / 2147483648.0
+    elif data.dtype == np.uint8:
+        x = (data.astype(np.float32) - 128.0) / 128.0
+    else:
+        x = data.astype(np.float32)
+    return torch.from_numpy(np.ascontiguousarray(x.T)), int(sr)
+
+
+def load_audio_tensor(waveform, orig_sample_rate, sample_rate=22050, cut_time_seconds=10):
+    """Everything ``load_audio`` does after ``torchaudio.load`` (``utilityFunctions.py:109-120``), on the device:
+    ``(C, L)`` at ``orig_sample_rate`` -> ``(1, L')`` at ``sample_rate`` for mono / stereo input."""
+    if waveform.ndim != 2:
+        raise ValueError(f"expected (channels, samples), got {tuple(waveform.shape)}")
+    if waveform.shape[0] not in (1, 2):
+        raise NotImplementedError("only mono and stereo files are handled on the device (the reference averages "
+                                  "exactly two channels, utilityFunctions.py:119)")
+    fe = default_frontend(_cuda_device(waveform))
+    out = fe.load_audio(waveform, orig_sample_rate, sample_rate, cut_time_seconds)
+    return out.to(_home(waveform)), sample_rate
+
+
+def load_audio(file_path, sample_rate=22050, cut_time_seconds=10):
+    """``utilityFunctions.load_audio`` (``utilityFunctions.py:105-122``): returns ``(waveform (1, L'), sample_rate)``."""
+    waveform, orig_sample_rate = _decode_file(file_path)
+    return load_audio_tensor(waveform, orig_sample_rate, sample_rate, cut_time_seconds)

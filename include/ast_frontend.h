@@ -192,6 +192,32 @@ int ast_stats_accumulate_features(const ast_plan* plan, const float* feats, cons
 /* host: mean = sum_mean / N, std = sqrt(sum_var / N) -> (2, 597) f32 each                   */
 int ast_stats_finalize(const double* host_acc_2x2x597, double count, float* host_mean, float* host_std);
 
+/* ---- audio loading: the step before the hot path ------------------------- */
+/*
+ * The device part of load_audio (utilityFunctions.py:105-122): zero-pad / cut each clip to cut_samples
+ * (= int(cut_time_seconds * orig_sr)), resample orig_sr -> new_sr exactly as
+ * torchaudio.functional.resample(waveform, orig_sr, new_sr) does with its defaults (sinc_interp_hann,
+ * lowpass_filter_width = 6, rolloff = 0.99), then average the two channels of a stereo clip
+ * (torch.mean(waveform, dim=0, keepdim=True), :119-120).  File decoding (torchaudio.load) stays on the host.
+ *
+ * An ast_resampler holds the polyphase taps of one (orig_sr, new_sr) pair on one device; immutable after creation.
+ *   wave        (B, C, in_stride) f32 device, C in {1, 2}; clip b holds lengths_in[b] valid samples per channel
+ *               (lengths_in == NULL: in_stride), samples past min(lengths_in[b], cut_samples) read as zeros
+ *   out         (B, out_stride) f32 device; ast_resample_length(cut_samples, ...) samples per clip are written
+ */
+typedef struct ast_resampler ast_resampler;
+/* reduced rates (divided by their gcd) and the half width of the FIR: taps per phase = 2 * width + orig_reduced */
+int ast_resample_geometry(int32_t orig_sr, int32_t new_sr, int32_t* orig_reduced, int32_t* new_reduced, int32_t* width);
+/* ceil(new * n_in / orig), the output length of torchaudio.functional.resample; -1 on invalid arguments */
+int64_t ast_resample_length(int64_t n_in, int32_t orig_sr, int32_t new_sr);
+/* host copy of the taps, (new_reduced, 2 * width + orig_reduced) f32, so a checker can compare them */
+int ast_host_resample_taps(int32_t orig_sr, int32_t new_sr, float* taps, int32_t capacity);
+int ast_resampler_create(int32_t orig_sr, int32_t new_sr, int32_t device, ast_resampler** resampler);
+int ast_resampler_destroy(ast_resampler* resampler);
+int ast_load_audio_forward(const ast_resampler* resampler, const float* wave, const int32_t* lengths_in,
+                           int32_t batch, int32_t channels, int64_t in_stride, int64_t cut_samples, float* out,
+                           int64_t out_stride, void* stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /*
  * Per-kernel device timing (no counterpart in the reference).  While enabled, every kernel launch
