@@ -42,6 +42,7 @@ BYTES_SECTIONS_STFT = 4 * 2 * 287 * 513 * 4
 BYTES_SECTIONS_CQT = 4 * 2 * 287 * 84 * 4
 BYTES_FEATURE_PATH = BYTES_WAVE + 4 * 2 * 287 * 597 * 4          # 6 365 008
 BYTES_ISTFT_PATH = BYTES_SECTIONS_STFT + 219904 * 4               # 5 591 008
+BYTES_LOAD_AUDIO = 2 * 441000 * 4 + CLIP_SAMPLES * 4              # 4 410 000: stereo 44.1 kHz in, mono 22.05 kHz out
 _OCT = [220500, 110250, 55125, 27563, 13782, 6891, 3446]
 KERNEL_BYTES_PER_CLIP = {  # compulsory input + output bytes of each kernel as the path is split today
     "stft_kernel": BYTES_WAVE + BYTES_SECTIONS_STFT,
@@ -285,6 +286,15 @@ def main():
     istft_value = world * CLIPS_PER_GPU * ISTFT_SECONDS / (ms_istft / 1e3)
     clocks.__exit__(None, None, None)
 
+    # ---- load_audio leg: (64, 2, 441000) stereo 44.1 kHz -> pad/cut + resample 2:1 + mono mix -> (64, 220500)
+    stereo = torch.randn((CLIPS_PER_GPU, 2, 441000), dtype=torch.float32, device=device) * 0.1
+
+    def load_step():
+        fe.load_audio(stereo, 44100, SAMPLE_RATE, 10)
+
+    ms_load = timed(load_step, args.steps, args.warmup) / args.steps
+    del stereo
+
     # ---- roofline pass: the same K steps with per-kernel CUDA events (ast_profile_*), rank-local
     lib.profile_enable(True)
     for _ in range(args.steps):
@@ -365,6 +375,11 @@ def main():
             "istft": {"metric": "audio-sec/sec iSTFT (merge + inverse STFT)", "value": istft_value, "unit": UNIT,
                       "ms_per_step": ms_istft, "gpu_launches": args.steps,
                       "workload": "configs[4] at B=64 per GPU: (64,4,2,287,513) -> (64,219904)"},
+            "load_audio": {"metric": "audio-sec/sec load_audio device part (pad/cut + 44.1k->22.05k resample + stereo mean)",
+                           "value": world * CLIPS_PER_GPU * CLIP_SECONDS / (ms_load / 1e3), "unit": UNIT,
+                           "ms_per_step": ms_load, "bytes_per_clip": BYTES_LOAD_AUDIO,
+                           "achieved_gbs": BYTES_LOAD_AUDIO * CLIPS_PER_GPU / (ms_load * 1e-3) / 1e9,
+                           "frac_of_hbm_peak": BYTES_LOAD_AUDIO * CLIPS_PER_GPU / (ms_load * 1e-3) / 1e9 / peak},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
