@@ -15,8 +15,8 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from .frontend import F_CQT, F_STFT, F_TOTAL, FrontEnd, default_frontend
-from .utilityFunctions import _cuda_device, _home
+from .frontend import F_CQT, F_STFT, F_TOTAL, SAMPLE_RATE, FrontEnd, default_frontend
+from .utilityFunctions import _cuda_device, _decode_file, _home
 
 DEFAULT_STATS_DIR = "train_set_stats"  # dataloader.py:43-44, :68
 
@@ -140,3 +140,97 @@ def collate_waveforms(piano_waves: Sequence[torch.Tensor], violin_waves: Sequenc
     p = torch.stack([w.reshape(-1) for w in piano_waves])
     v = torch.stack([w.reshape(-1) for w in violin_waves])
     return batcher(p, v)
+
+
+# --------------------------------------------------------------------------------------------
+# DualInstrumentDataset / get_dataloader (dataloader.py:20-121, :149-172) on the device
+# --------------------------------------------------------------------------------------------
+def _list_audio(directory: str):
+    # dataloader.py:22-31: sorted, ".mp3" or ".wav"
+    return sorted(os.path.join(directory, f) for f in os.listdir(directory) if f.endswith(".mp3") or f.endswith(".wav"))
+
+
+def load_clips(paths: Sequence[str], fe: FrontEnd, sample_rate: int = SAMPLE_RATE, cut_time_seconds: float = 10) -> torch.Tensor:
+    """``load_audio`` for a list of files -> ``(len(paths), L')`` float32 on the device.  Files are decoded on the
+    host and grouped by (channels, rate) so that each group is ONE device call (pad / cut + resample + mono mix)."""
+    decoded = [_decode_file(p) for p in paths]
+    out = None
+    groups = {}
+    for i, (w, sr) in enumerate(decoded):
+        groups.setdefault((int(w.shape[0]), int(sr)), []).append(i)
+    for (channels, sr), idx in groups.items():
+        cut = int(cut_time_seconds * sr)
+        n_max = min(max(int(decoded[i][0].shape[1]) for i in idx), cut)
+        batch = torch.zeros((len(idx), channels, max(n_max, 1)), dtype=torch.float32)
+        lengths = torch.zeros(len(idx), dtype=torch.int32)
+        for k, i in enumerate(idx):
+            n = min(int(decoded[i][0].shape[1]), cut)
+            batch[k, :, :n] = decoded[i][0][:, :n]
+            lengths[k] = n
+        y = fe.load_audio(batch, sr, sample_rate, cut_time_seconds, lengths=lengths)
+        if out is None:
+            out = torch.empty((len(paths), y.shape[1]), dtype=torch.float32, device=fe.device)
+        if y.shape[1] != out.shape[1]:
+            raise ValueError("files of different rates must resample to the same clip length")
+        out[torch.tensor(idx, device=fe.device)] = y
+    return out
+
+
+class DualInstrumentDataset:
+    """``dataloader.DualInstrumentDataset`` (``dataloader.py:20-121``) with the same constructor, file listing and
+    statistics handling; ``__getitem__`` returns the reference's dict, computed by the device path."""
+
+    def __init__(self, piano_dir, violin_dir, stats_path=None, use_separate_stats=True, stats_dir: str = DEFAULT_STATS_DIR,
+                 device=None):
+        self.piano_files = _list_audio(piano_dir)
+        self.violin_files = _list_audio(violin_dir)
+        self.length = min(len(self.piano_files), len(self.violin_files))
+        self.use_separate_stats = use_separate_stats
+        self.batcher = SpectralBatcher(stats_path, use_separate_stats, stats_dir, device)
+
+    def __len__(self):
+        return self.length
+
+    def waves(self, indices: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:
+        fe = self.batcher.fe
+        both = load_clips([self.piano_files[i] for i in indices] + [self.violin_files[i] for i in indices], fe)
+        return both[: len(indices)], both[len(indices):]
+
+    def __getitem__(self, idx):
+        p, v = self.waves([idx])
+        feats, _ = self.batcher(p, v)
+        return {"piano": feats[0], "violin": feats[1], "piano_label": 0, "violin_label": 1}
+
+
+class GpuDataLoader:
+    """What ``get_dataloader`` returns: an iterable of ``((B, S, 2, 287, 597) float32, (B,) int64)`` batches.
+
+    Batch composition follows the reference exactly: ``DataLoader(batch_size=B, drop_last=True)`` hands B items
+    to ``custom_collate_fn``, which keeps the first B/2 of them (``dataloader.py:133-136``) - so batch k holds the
+    piano and the violin clips of items ``order[k B : k B + B/2]``.  Only those B/2 items are decoded and
+    transformed here (the reference also transforms, then discards, the other half)."""
+
+    def __init__(self, dataset: DualInstrumentDataset, batch_size: int, shuffle: bool, generator: Optional[torch.Generator] = None):
+        self.dataset, self.batch_size, self.shuffle, self.generator = dataset, int(batch_size), bool(shuffle), generator
+
+    def __len__(self):
+        return len(self.dataset) // self.batch_size if self.batch_size > 0 else 0
+
+    def __iter__(self):
+        n = len(self.dataset)
+        order = torch.randperm(n, generator=self.generator).tolist() if self.shuffle else list(range(n))
+        half = self.batch_size // 2
+        for k in range(len(self)):
+            items = order[k * self.batch_size: k * self.batch_size + half]
+            p, v = self.dataset.waves(items)
+            yield self.dataset.batcher(p, v)
+
+
+def get_dataloader(piano_dir, violin_dir, batch_size=8, shuffle=True, stats_path=None, use_separate_stats=True):
+    """``dataloader.get_dataloader`` (``dataloader.py:149-172``), same arguments and batch layout; batches are
+    produced in device memory."""
+    if batch_size % 2 != 0:
+        print(f"Warning: batch_size={batch_size} is odd. Rounding down to {batch_size-1} for balanced batches.")
+        batch_size = batch_size - 1
+    dataset = DualInstrumentDataset(piano_dir, violin_dir, stats_path, use_separate_stats)
+    return GpuDataLoader(dataset, batch_size, shuffle)

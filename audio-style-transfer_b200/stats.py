@@ -93,3 +93,53 @@ def write_reference_npz(out_dir: str, results: Dict[str, Tuple[np.ndarray, np.nd
         paths[key] = os.path.join(out_dir, names.get(key, f"stats_{key}.npz"))
         save_stats_npz(paths[key], mean, std)
     return paths
+
+
+def main(argv=None) -> int:
+    """``compute_separated_stats.py`` / ``compute_unified_stats.py`` as one command (SURVEY.md 8f-3)::
+
+        python -m audio_style_transfer_b200.stats --piano-dir D1 --violin-dir D2 --out-dir train_set_stats [--batch 32]
+
+    Every rank of a ``torchrun`` launch takes a contiguous shard of each file list (one all-reduce at the end);
+    rank 0 writes ``stats_stft_cqt_piano.npz``, ``stats_stft_cqt_violin.npz`` and ``stats_unified_stft_cqt.npz``
+    with the keys ``DualInstrumentDataset`` loads."""
+    import argparse
+    import os
+
+    import torch.distributed as dist
+
+    from .dataloader import _list_audio, load_clips
+
+    ap = argparse.ArgumentParser(description=main.__doc__)
+    ap.add_argument("--piano-dir", required=True)
+    ap.add_argument("--violin-dir", required=True)
+    ap.add_argument("--out-dir", default="train_set_stats")
+    ap.add_argument("--batch", type=int, default=32)
+    args = ap.parse_args(argv)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    fe = FrontEnd(torch.device("cuda", local))
+    lists = [_list_audio(args.piano_dir), _list_audio(args.violin_dir)]
+
+    def batches():
+        for g, files in enumerate(lists):
+            mine = [files[i] for i in shard_range(len(files), rank, world)]
+            for k in range(0, len(mine), args.batch):
+                wave = load_clips(mine[k: k + args.batch], fe)
+                yield wave, torch.full((wave.shape[0],), g, dtype=torch.int32, device=fe.device)
+
+    acc, counts = compute_stats(fe, batches(), n_groups=2)
+    if rank == 0:
+        paths = write_reference_npz(args.out_dir, finalize_all(acc, counts))
+        for key, path in paths.items():
+            print(f"{key}: {path}")
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
