@@ -151,7 +151,7 @@ int launch_prep_stats(const float* mean, const float* std, float eps, int n, flo
 int launch_count_sections(const int32_t* lengths, int batch, long long max_samples, int layout, int dim1,
                           int window, int overlap, int32_t* n_out, cudaStream_t st);
 int launch_stft(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
-                long long wave_stride, const OutSpec& out, cudaStream_t st);
+                long long wave_stride, const OutSpec& out, cudaStream_t st, int pad_zero = 0);
 int launch_decimate_cascade(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch,
                             long long max_samples, long long wave_stride, float* ws, long long ws_clip_stride,
                             cudaStream_t st);

@@ -29,6 +29,7 @@ struct StftParams {
   const float2* t2;
   const float* hann;
   int overlap;
+  int pad_zero;         // 0: reflect padding (torch.stft, get_STFT); 1: zero padding (librosa.stft default, mse_spectrogram)
   OutSpec out;
 };
 
@@ -71,7 +72,8 @@ struct StftEmit {
   }
 };
 
-__device__ __forceinline__ float load_reflect(const float* __restrict__ x, int i, int len) {
+__device__ __forceinline__ float load_reflect(const float* __restrict__ x, int i, int len, int pad_zero) {
+  if (pad_zero) return (i >= 0 && i < len) ? __ldg(x + i) : 0.f;  // librosa.stft(center=True, pad_mode="constant")
   // torch.stft(center=True, pad_mode="reflect"): one reflection suffices because len > n_fft / 2
   if (i < 0) i = -i;
   if (i >= len) i = 2 * (len - 1) - i;
@@ -155,8 +157,8 @@ __global__ void __launch_bounds__(kStftThreads, 3) stft_kernel(const StftParams 
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
           const int i = base + 64 * n1;
-          const float xa = load_reflect(x, i, len);
-          const float xb = live_b ? load_reflect(x, i + kHop, len) : 0.f;
+          const float xa = load_reflect(x, i, len, p.pad_zero);
+          const float xb = live_b ? load_reflect(x, i + kHop, len, p.pad_zero) : 0.f;
           v[n1] = make_float2(xa * win[n1], xb * win[n1]);
         }
       }
@@ -197,8 +199,9 @@ int stft_init() {
 }
 
 int launch_stft(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
-                long long wave_stride, const OutSpec& out, cudaStream_t st) {
+                long long wave_stride, const OutSpec& out, cudaStream_t st, int pad_zero) {
   StftParams p;
+  p.pad_zero = pad_zero;
   p.wave = wave;
   p.lengths = lengths;
   p.max_samples = max_samples;

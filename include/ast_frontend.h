@@ -218,6 +218,17 @@ int ast_load_audio_forward(const ast_resampler* resampler, const float* wave, co
                            int32_t batch, int32_t channels, int64_t in_stride, int64_t cut_samples, float* out,
                            int64_t out_stride, void* stream);
 
+/* ---- evaluation metric on the far side of the iSTFT ----------------------- */
+/*
+ * replaces mse_spectrogram (evaluation_reconstruction.py:105-118, evaluation_style_transfer.py:111-119):
+ * mean over (513, T) of (|librosa.stft(a, n_fft=1024, hop_length=256)| - |librosa.stft(b, ...)|)^2 with
+ * T = min(T_a, T_b); librosa.stft defaults: center=True with ZERO padding, periodic Hann window.
+ *   a, b     mono signals on the device (n_a, n_b samples, both >= 1); result: 1 double on the device
+ */
+size_t ast_mse_workspace_bytes(const ast_plan* plan, int64_t n_a, int64_t n_b);
+int ast_mse_spectrogram(const ast_plan* plan, const float* a, int64_t n_a, const float* b, int64_t n_b,
+                        void* workspace, size_t workspace_bytes, double* result, void* stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /*
  * Per-kernel device timing (no counterpart in the reference).  While enabled, every kernel launch
