@@ -53,6 +53,29 @@ struct ProfileSpan {
       return ::ast::fail(AST_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(err__)); \
   } while (0)
 
+// Programmatic dependent launch: the kernel may start (prologue: shared-memory tables, TMEM allocation, barrier
+// init) while the previous kernel of the stream is still draining; it must execute pdl_wait() before touching
+// anything the previous kernel reads or writes.  Off while profiling (events between launches would serialise).
+template <class Params>
+inline cudaError_t launch_with_pdl(void (*kernel)(Params), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                                   const Params& params) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = profile_on() ? 0 : 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, params);
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 // ---- host-side constant derivation (plan.cu; double precision, no CUDA) -------------------
 void host_hann(double* w, int n);
 void host_decimator_taps(double* taps);                 // kDecTaps, unit DC gain

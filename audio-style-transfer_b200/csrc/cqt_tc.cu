@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  pdl_launch_dependents();
   // B images: resident for the CTA's lifetime
   for (int i = tid; i < kBFloats / 4; i += kThreads)
     reinterpret_cast<float4*>(b_img)[i] = __ldg(reinterpret_cast<const float4*>(p.bmat) + i);
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
   __syncthreads();
   umma::fence_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the octave signals come from the decimator launches just before this one
   const int total = p.tiles_per_clip_oct * kOctaves * p.batch;  // gridDim.x <= total
 
   if (warp < kProducers / 32) {
@@ -531,8 +533,7 @@ int launch_cqt_tc(const ast_plan* plan, const float* wave, const int32_t* length
   long long ctas = (long long)p.tiles_per_clip_oct * kOctaves * batch;
   if (ctas > plan->sm_count) ctas = plan->sm_count;  // persistent: one CTA per SM
   ProfileSpan span("cqt_tc_kernel", st);
-  cqt_tc_kernel<<<(unsigned)ctas, cqt_tc::kThreads, cqt_tc::kSmem, st>>>(p);
-  AST_LAUNCH_CHECK("cqt_tc_kernel");
+  AST_CUDA_TRY(launch_with_pdl(cqt_tc_kernel, (unsigned)ctas, cqt_tc::kThreads, cqt_tc::kSmem, st, p));
   return AST_OK;
 }
 

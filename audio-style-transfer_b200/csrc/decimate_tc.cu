@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  pdl_launch_dependents();  // the next stage may start its prologue as soon as SMs free up
   for (int i = tid; i < kStripFloats / 4; i += kThreads) {
     reinterpret_cast<float4*>(t_hi)[i] = __ldg(reinterpret_cast<const float4*>(p.strip_hi) + i);
     reinterpret_cast<float4*>(t_lo)[i] = __ldg(reinterpret_cast<const float4*>(p.strip_lo) + i);
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
   __syncthreads();
   umma::fence_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything below reads the previous stage's output / overwrites buffers its predecessors read
   const int total = p.tiles_per_clip * p.batch;
   int tile = blockIdx.x;
   if (tile < total && !dtc_decode(p, tile).live) tile = dtc_next_live(p, tile, total);
@@ -371,8 +373,7 @@ int launch_decimate2_tc(const ast_plan* plan, const float* in, long long in_stri
   if (ctas > plan->sm_count) ctas = plan->sm_count;  // persistent: one CTA per SM
   if (ctas == 0) return AST_OK;
   ProfileSpan span("decimate2_tc_kernel", st);
-  decimate2_tc_kernel<<<(unsigned)ctas, dtc::kThreads, dtc::kSmem, st>>>(p);
-  AST_LAUNCH_CHECK("decimate2_tc_kernel");
+  AST_CUDA_TRY(launch_with_pdl(decimate2_tc_kernel, (unsigned)ctas, dtc::kThreads, dtc::kSmem, st, p));
   return AST_OK;
 }
 
