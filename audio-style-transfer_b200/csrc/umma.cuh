@@ -158,15 +158,21 @@ __device__ __forceinline__ void split_tf32(const float4& v, float4& h, float4& l
   l.x = v.x - h.x, l.y = v.y - h.y, l.z = v.z - h.z, l.w = v.w - h.w;
 }
 
-// x[s .. s+3] with zeros outside [0, len)
-__device__ __forceinline__ float4 load4_zero_ext(const float* __restrict__ x, int s, int len, bool vec_ok) {
-  if (s >= 0 && s + 3 < len && vec_ok) return __ldg(reinterpret_cast<const float4*>(x + s));
+// x[s .. s+3] with zeros outside [0, len).  A chunk is almost always entirely inside or entirely outside the
+// signal; the straddling case (at most two chunks per staged block) is kept out of line so that unrolled staging
+// loops stay small - the inlined scalar path made the producers of the tensor-core kernels instruction-bound.
+static __device__ __noinline__ float4 load4_partial(const float* __restrict__ x, int s, int len) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (s >= 0 && s < len) v.x = __ldg(x + s);
   if (s + 1 >= 0 && s + 1 < len) v.y = __ldg(x + s + 1);
   if (s + 2 >= 0 && s + 2 < len) v.z = __ldg(x + s + 2);
   if (s + 3 >= 0 && s + 3 < len) v.w = __ldg(x + s + 3);
   return v;
+}
+__device__ __forceinline__ float4 load4_zero_ext(const float* __restrict__ x, int s, int len, bool vec_ok) {
+  if (s >= 0 && s + 3 < len && vec_ok) return __ldg(reinterpret_cast<const float4*>(x + s));
+  if (s + 3 < 0 || s >= len) return make_float4(0.f, 0.f, 0.f, 0.f);
+  return load4_partial(x, s, len);
 }
 
 }  // namespace umma
