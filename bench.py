@@ -308,6 +308,8 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+    # TF32 dense peak = half the measured bf16 cuBLAS burst figure (same tensor pipe, half the rate)
+    tf32_peak = float(json.load(open(peaks_path)).get("bf16_tflops", 0.0)) / 2 if os.path.exists(peaks_path) else 1590.0 / 2
     kernels = {}
     feature_ms = 0.0
     for name, (tot, n) in prof.items():
@@ -316,7 +318,10 @@ def main():
         kernels[name] = {"avg_ms": avg, "launches_per_step": n / args.steps, "ms_per_step": tot / args.steps,
                          "achieved_gbs": nbytes / (avg * 1e-3) / 1e9 if avg > 0 else None}
         if name in TENSOR_FLOPS_PER_CLIP and avg > 0:
-            kernels[name]["tensor_tflops_tf32_issued"] = TENSOR_FLOPS_PER_CLIP[name] * CLIPS_PER_GPU / (avg * 1e-3) / 1e12
+            tf = TENSOR_FLOPS_PER_CLIP[name] * CLIPS_PER_GPU / (avg * 1e-3) / 1e12
+            kernels[name]["tensor_tflops_tf32_issued"] = tf
+            if tf32_peak:
+                kernels[name]["tensor_frac_of_tf32_peak"] = tf / tf32_peak
         if name != "istft_kernel":
             feature_ms += tot / args.steps
     feat_kernels = {k: v for k, v in kernels.items() if k != "istft_kernel"}
@@ -324,8 +329,13 @@ def main():
     roofline = None
     if dom:
         a = kernels[dom]["achieved_gbs"]
+        # DRAM bytes per launch of each kernel at this workload, from the committed ncu --set full capture
+        traffic = None
+        traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(traffic_path):
+            traffic = json.load(open(traffic_path)).get("dram_bytes_per_launch", {}).get(dom)
         roofline = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": traffic, "peak_source": peak_src,
                     "share_of_step": kernels[dom]["ms_per_step"] / feature_ms if feature_ms else None,
                     "path": {"bytes_per_clip": BYTES_FEATURE_PATH,
                              "achieved": BYTES_FEATURE_PATH * CLIPS_PER_GPU / (ms_step * 1e-3) / 1e9,
