@@ -44,6 +44,7 @@ static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 struct Workspace {
   float2* stats_table;  // batch * 2 * 597 (mean, rstd)
   float* octaves;       // batch * cqt_ws_clip_stride floats
+  int* dec_flags;       // the decimator's per-tile completion counters
   size_t used;
 };
 
@@ -52,14 +53,17 @@ static size_t octave_bytes(int batch, long long max_samples) {
   return align_up(sizeof(float) * (size_t)cqt_ws_clip_stride(max_samples) * (size_t)batch);
 }
 
+static size_t flag_bytes(int batch, long long max_samples) { return align_up(decimator_flag_bytes(batch, max_samples)); }
+
 static int carve(void* ws, size_t ws_bytes, int batch, long long max_samples, Workspace* w) {
-  const size_t need = stats_table_bytes(batch) + octave_bytes(batch, max_samples);
+  const size_t need = stats_table_bytes(batch) + octave_bytes(batch, max_samples) + flag_bytes(batch, max_samples);
   if (!ws || ws_bytes < need)
     return fail(AST_ERR_WORKSPACE, "workspace of %zu bytes is too small, need %zu (ast_workspace_bytes)", ws_bytes, need);
   if (reinterpret_cast<uintptr_t>(ws) & 255) return fail(AST_ERR_INVALID_ARG, "workspace must be 256-byte aligned");
   char* p = static_cast<char*>(ws);
   w->stats_table = reinterpret_cast<float2*>(p);
   w->octaves = reinterpret_cast<float*>(p + stats_table_bytes(batch));
+  w->dec_flags = reinterpret_cast<int*>(p + stats_table_bytes(batch) + octave_bytes(batch, max_samples));
   w->used = need;
   return AST_OK;
 }
@@ -101,7 +105,7 @@ extern "C" {
 size_t ast_workspace_bytes(const ast_plan* plan, int32_t batch, int64_t max_samples) {
   (void)plan;
   if (batch < 0 || max_samples < 0) return 0;
-  return stats_table_bytes(batch) + octave_bytes(batch, max_samples);
+  return stats_table_bytes(batch) + octave_bytes(batch, max_samples) + flag_bytes(batch, max_samples);
 }
 
 size_t ast_stats_workspace_bytes(const ast_plan* plan, int32_t batch, int64_t max_samples) {
@@ -130,7 +134,7 @@ int ast_cqt_forward(const ast_plan* plan, const float* wave, const int32_t* leng
   if (rc != AST_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const long long ws_stride = cqt_ws_clip_stride(max_samples);
-  rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, st);
+  rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, st);
   if (rc != AST_OK) return rc;
   OutSpec o = make_out(plan, out, AST_LAYOUT_FLAT, t_out, kFCqt, 0);  // 84-wide rows, CQT bin 0 at column 0
   return launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, o, st);
@@ -176,7 +180,7 @@ int ast_features_forward(const ast_plan* plan, const float* wave, const int32_t*
   if (!g_overlap_streams || profile_on()) {
     rc = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st);
     if (rc != AST_OK) return rc;
-    rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, st);
+    rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, st);
     if (rc != AST_OK) return rc;
     return launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, oq, st);
   }
@@ -187,7 +191,7 @@ int ast_features_forward(const ast_plan* plan, const float* wave, const int32_t*
   AST_CUDA_TRY(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming));
   AST_CUDA_TRY(cudaEventRecord(fork_ev, st));
   AST_CUDA_TRY(cudaStreamWaitEvent(plan->side_stream, fork_ev, 0));
-  rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, plan->side_stream);
+  rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, plan->side_stream);
   if (rc == AST_OK) rc = launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, oq, plan->side_stream);
   int rc2 = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st);
   cudaEventRecord(join_ev, plan->side_stream);

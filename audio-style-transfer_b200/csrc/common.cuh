@@ -177,7 +177,7 @@ int launch_stft(const ast_plan* plan, const float* wave, const int32_t* lengths,
                 long long wave_stride, const OutSpec& out, cudaStream_t st, int pad_zero = 0);
 int launch_decimate_cascade(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch,
                             long long max_samples, long long wave_stride, float* ws, long long ws_clip_stride,
-                            cudaStream_t st);
+                            int* flags, cudaStream_t st);
 int launch_cqt(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
                long long wave_stride, const float* ws, long long ws_clip_stride, const OutSpec& out, cudaStream_t st);
 int launch_istft(const ast_plan* plan, const float* spec, int batch, int dim1, int f_in, int layout, int window,
@@ -199,9 +199,10 @@ void set_overlap_streams(int on);
 bool use_tc_cqt();
 int decimator_strip_floats();
 void host_decimator_strip(const double* taps_scaled, float* strip_hi, float* strip_lo);  // decimator_strip_floats() each
-int launch_decimate2_tc(const ast_plan* plan, const float* in, long long in_stride, float* out, long long out_stride,
-                        const int32_t* lengths, long long max_samples, int in_octave, int batch, bool vec_ok,
-                        cudaStream_t st);
+size_t decimator_flag_bytes(int batch, long long max_samples);
+int launch_decimate_cascade_tc(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch,
+                               long long max_samples, long long wave_stride, float* ws, long long ws_clip_stride,
+                               int* flags, cudaStream_t st);
 void set_tc_decimator(int on);
 int istft_init();  // into __constant__ memory of decimate.cu
 

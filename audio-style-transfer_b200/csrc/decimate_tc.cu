@@ -24,6 +24,15 @@
 // relative per accumulating MMA at full magnitude), so per tile the 32 small cross-term MMAs (lo*hi, hi*lo) are
 // issued FIRST - their truncation error scales with the still tiny accumulator - and the 16 hi*hi MMAs last.
 //
+// All six stages of the cascade run in ONE persistent launch: tiles are numbered stage by stage (stage, clip, tile in
+// clip) and dealt round-robin to the CTAs; a tile of stage s + 1 waits for the (at most three) stage-s tiles that
+// produce its input through per-tile completion counters in the workspace (release: __threadfence + atomicAdd by
+// each of the four epilogue warps; acquire: ld.acquire.gpu polling by one lane per producer warp, bounded).  Every
+// dependency points to an earlier tile number and each CTA walks its tiles in order, so the earliest unfinished
+// tile can always run; stage boundaries cost nothing (the tail of stage s overlaps the head of stage s + 1) and five
+// launches disappear.  Inputs produced by this launch are read with ld.global.cg (L2), never through L1 / the
+// non-coherent path.
+//
 // One persistent CTA per SM, 13 warps:
 //   warps 0-7   producers: the NEXT tile's 64 KB of samples are loaded into registers (16 x LDG.128 per thread) while
 //               the current one is stored: raw -> A_hi (two whole tiles resident), x - trunc(x) -> A_lo (2-stage
@@ -68,17 +77,21 @@ constexpr int kEpiFloats = 4 * 32 * kEpiStride;  // one [32 rows][68] transpose 
 constexpr size_t kSmem = sizeof(float) * (2 * kTileFloats + 2 * kSliceFloats + 2 * kStripFloats + kEpiFloats) + 128;
 }  // namespace dtc
 
+constexpr int kDecStages = kOctaves - 1;  // 6
+
 struct DecimateTcParams {
-  const float* in;
-  long long in_stride;
-  float* out;
-  long long out_stride;
+  const float* wave;       // octave 0: clip b at wave + b * wave_stride
+  long long wave_stride;
+  float* ws;               // octaves 1..6: clip b, octave i at ws + b * ws_clip_stride + oct_off[i]
+  long long ws_clip_stride;
+  long long oct_off[kOctaves];
   const int32_t* lengths;
   long long max_samples;
-  int in_octave;
   int batch;
-  int tiles_per_clip;
-  bool vec_ok;
+  int tiles_per_clip[kDecStages];
+  int tile_prefix[kDecStages + 1];   // first tile number of each stage; [6] = total
+  bool vec_ok0;                      // 16-byte loads legal on the octave-0 rows
+  int* flags;                        // [stage][clip][tile of stage 0's count]: epilogue warps that finished the tile (4 = done)
   const float* strip_hi;   // [2][320][4] smem image of the Toeplitz strip (TF32-exact values)
   const float* strip_lo;
 };
@@ -88,24 +101,34 @@ struct DtcTile {
   float* y;
   int len_in, len_out;
   int row0;        // first row of the tile (rows advance by 116 per tile)
+  int stage, clip, k;
   bool live;       // false: the tile lies past the clip's end (ragged batch)
-  bool interior;   // every staged sample lies inside [0, len_in) and 16-byte copies are legal
+  bool interior;   // every staged sample lies inside [0, len_in) and 16-byte loads are legal
+  bool vec_ok;
 };
 
 __device__ __forceinline__ DtcTile dtc_decode(const DecimateTcParams& p, int tile) {
   using namespace dtc;
   DtcTile t;
-  const int b = tile / p.tiles_per_clip;
-  t.row0 = (tile - b * p.tiles_per_clip) * kRowsOut;
+  int s = 0;
+#pragma unroll
+  for (int i = 1; i < kDecStages; ++i) s += tile >= p.tile_prefix[i] ? 1 : 0;
+  const int r = tile - p.tile_prefix[s];
+  const int b = r / p.tiles_per_clip[s];
+  t.stage = s;
+  t.clip = b;
+  t.k = r - b * p.tiles_per_clip[s];
+  t.row0 = t.k * kRowsOut;
   const long long len0 = p.lengths ? p.lengths[b] : p.max_samples;
-  t.len_in = (int)((len0 + (1LL << p.in_octave) - 1) >> p.in_octave);
+  t.len_in = (int)((len0 + (1LL << s) - 1) >> s);
   t.len_out = (t.len_in + 1) >> 1;
   t.live = t.row0 * kP < t.len_out;
-  t.x = p.in + (long long)b * p.in_stride;
-  t.y = p.out + (long long)b * p.out_stride;
+  t.x = s == 0 ? p.wave + (long long)b * p.wave_stride : p.ws + (long long)b * p.ws_clip_stride + p.oct_off[s];
+  t.y = p.ws + (long long)b * p.ws_clip_stride + p.oct_off[s + 1];
+  t.vec_ok = s > 0 || p.vec_ok0;
   const int first = kRS * t.row0 - kDecHalf;
   const int last = kRS * (t.row0 + kGroupValid * (kGroups - 1) + 31) - kDecHalf + kRS;  // one past the last staged sample
-  t.interior = first >= 0 && last <= t.len_in && p.vec_ok;
+  t.interior = first >= 0 && last <= t.len_in && t.vec_ok;
   return t;
 }
 
@@ -115,20 +138,83 @@ __device__ __forceinline__ int dtc_next_live(const DecimateTcParams& p, int tile
   return -1;
 }
 
+__device__ __forceinline__ int* dtc_flag(const DecimateTcParams& p, int stage, int clip, int k) {
+  return p.flags + ((long long)stage * p.batch + clip) * p.tiles_per_clip[0] + k;
+}
+
+// The stage s - 1 tiles whose outputs tile t (stage s >= 1) stages: output indices [lo, hi) -> tiles lo / 7424 ...
+__device__ __forceinline__ void dtc_dep_range(const DtcTile& t, int& k_lo, int& k_hi) {
+  using namespace dtc;
+  int lo = kRS * t.row0 - kDecHalf, hi = kRS * (t.row0 + kGroupValid * (kGroups - 1) + 32) - kDecHalf;
+  if (lo < 0) lo = 0;
+  if (hi > t.len_in) hi = t.len_in;
+  k_lo = lo / (kRowsOut * kP);
+  k_hi = hi > lo ? (hi - 1) / (kRowsOut * kP) : k_lo - 1;
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+
+// true when every producer tile of t has been completed by its four epilogue warps (one lane polls for the warp)
+__device__ __forceinline__ bool dtc_deps_ready(const DecimateTcParams& p, const DtcTile& t, int lane) {
+  if (t.stage == 0) return true;
+  int k_lo, k_hi;
+  dtc_dep_range(t, k_lo, k_hi);
+  int ok = 1;
+  if (lane == 0)
+    for (int k = k_lo; k <= k_hi; ++k) ok &= ld_acquire_gpu(dtc_flag(p, t.stage - 1, t.clip, k)) >= 4 ? 1 : 0;
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  return ok != 0;
+}
+
+// Bounded wait: a broken dependency chain traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void dtc_deps_wait(const DecimateTcParams& p, const DtcTile& t, int lane) {
+  for (uint32_t spin = 0; !dtc_deps_ready(p, t, lane); ++spin) {
+    __nanosleep(200);
+    if (spin > (1u << 24)) __trap();
+  }
+}
+
+__device__ __forceinline__ float4 ld_cg_f4(const float* ptr) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_cg_f(const float* ptr) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(ptr) : "memory");
+  return v;
+}
+// x[s .. s + 3] with zeros outside [0, len), through L2 (the data may have been written by this launch)
+static __device__ __noinline__ float4 dtc_load4_partial(const float* x, int s, int len) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s >= 0 && s < len) v.x = ld_cg_f(x + s);
+  if (s + 1 >= 0 && s + 1 < len) v.y = ld_cg_f(x + s + 1);
+  if (s + 2 >= 0 && s + 2 < len) v.z = ld_cg_f(x + s + 2);
+  if (s + 3 >= 0 && s + 3 < len) v.w = ld_cg_f(x + s + 3);
+  return v;
+}
+__device__ __forceinline__ float4 dtc_load4(const float* x, int s, int len, bool vec_ok) {
+  if (s >= 0 && s + 3 < len && vec_ok) return ld_cg_f4(x + s);
+  if (s + 3 < 0 || s >= len) return make_float4(0.f, 0.f, 0.f, 0.f);
+  return dtc_load4_partial(x, s, len);
+}
+
 // One 32-sample slice of a tile for this producer thread: chunk c = tid & 7 of rows (tid >> 3) + 32 i, i = 0..3
 // (row group i), read at sample 128 (row0 + 29 i + (tid >> 3)) - 192 + 32 s + 4 c.
 template <int S>
-__device__ __forceinline__ void dtc_load_slice(const DtcTile& t, int tid, bool vec_ok, float4 (&v)[16]) {
+__device__ __forceinline__ void dtc_load_slice(const DtcTile& t, int tid, float4 (&v)[16]) {
   using namespace dtc;
   const int a0 = kRS * (t.row0 + (tid >> 3)) - kDecHalf + 32 * S + 4 * (tid & 7);
   if (t.interior) {
 #pragma unroll
-    for (int i = 0; i < kChunksPerThread; ++i)
-      v[4 * S + i] = __ldg(reinterpret_cast<const float4*>(t.x + a0 + kRS * kGroupValid * i));
+    for (int i = 0; i < kChunksPerThread; ++i) v[4 * S + i] = ld_cg_f4(t.x + a0 + kRS * kGroupValid * i);
   } else {
 #pragma unroll
-    for (int i = 0; i < kChunksPerThread; ++i)
-      v[4 * S + i] = umma::load4_zero_ext(t.x, a0 + kRS * kGroupValid * i, t.len_in, vec_ok);
+    for (int i = 0; i < kChunksPerThread; ++i) v[4 * S + i] = dtc_load4(t.x, a0 + kRS * kGroupValid * i, t.len_in, t.vec_ok);
   }
 }
 
@@ -170,7 +256,7 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
   umma::fence_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything below reads the previous stage's output / overwrites buffers its predecessors read
-  const int total = p.tiles_per_clip * p.batch;
+  const int total = p.tile_prefix[kDecStages];
   int tile = blockIdx.x;
   if (tile < total && !dtc_decode(p, tile).live) tile = dtc_next_live(p, tile, total);
 
@@ -181,14 +267,19 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
     DtcTile cur;
     if (tile >= 0 && tile < total) {
       cur = dtc_decode(p, tile);
-      dtc_load_slice<0>(cur, tid, p.vec_ok, v);
-      dtc_load_slice<1>(cur, tid, p.vec_ok, v);
-      dtc_load_slice<2>(cur, tid, p.vec_ok, v);
-      dtc_load_slice<3>(cur, tid, p.vec_ok, v);
+      dtc_deps_wait(p, cur, lane);
+      dtc_load_slice<0>(cur, tid, v);
+      dtc_load_slice<1>(cur, tid, v);
+      dtc_load_slice<2>(cur, tid, v);
+      dtc_load_slice<3>(cur, tid, v);
     }
     for (int n = 0; tile >= 0 && tile < total; ++n) {
       const int next = dtc_next_live(p, tile, total);
-      if (next >= 0) cur = dtc_decode(p, next);
+      bool refill = false;  // the next tile's inputs exist already: load them slice by slice while this one is staged
+      if (next >= 0) {
+        cur = dtc_decode(p, next);
+        refill = dtc_deps_ready(p, cur, lane);
+      }
       // this A_hi buffer is free once the MMAs of tile n - 2 have completed
       umma::mbar_wait(h_empty + (n & 1), ((n >> 1) & 1) ^ 1);
       float4* hi_tile = reinterpret_cast<float4*>(a_hi + (n & 1) * kTileFloats);
@@ -210,12 +301,19 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
         if (lane == 0) umma::mbar_arrive(l_full + st);
         // refill the freed registers with the next tile (measured: better than loading the whole tile after the
         // last slice, although each fence.proxy.async then also waits for the previous slice's loads)
-        if (next >= 0) dtc_load_slice<S>(cur, tid, p.vec_ok, v);
+        if (refill) dtc_load_slice<S>(cur, tid, v);
       };
       stage(std::integral_constant<int, 0>{});
       stage(std::integral_constant<int, 1>{});
       stage(std::integral_constant<int, 2>{});
       stage(std::integral_constant<int, 3>{});
+      if (next >= 0 && !refill) {  // its producers were still running: wait for them now, then load the whole tile
+        dtc_deps_wait(p, cur, lane);
+        dtc_load_slice<0>(cur, tid, v);
+        dtc_load_slice<1>(cur, tid, v);
+        dtc_load_slice<2>(cur, tid, v);
+        dtc_load_slice<3>(cur, tid, v);
+      }
       tile = next;
     }
   } else if (warp == kMmaWarp) {
@@ -310,7 +408,13 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
           if (j + 2 < t.len_out) t.y[j + 2] = val.z;
         }
       }
-      __syncwarp();  // the staging buffer is rewritten by the next tile
+      // publish: this warp's rows of the tile are in global memory (stages 0..4 feed another stage of this launch)
+      __threadfence();
+      __syncwarp();  // also: the staging buffer is rewritten by the next tile
+      if (lane == 0 && t.stage < kDecStages - 1) {
+        __threadfence();
+        atomicAdd(dtc_flag(p, t.stage, t.clip, t.k), 1);
+      }
     }
   }
   umma::fence_before_thread_sync();
@@ -351,27 +455,43 @@ void host_decimator_strip(const double* taps_scaled, float* strip_hi, float* str
       }
 }
 
-int launch_decimate2_tc(const ast_plan* plan, const float* in, long long in_stride, float* out, long long out_stride,
-                        const int32_t* lengths, long long max_samples, int in_octave, int batch, bool vec_ok,
-                        cudaStream_t st) {
+size_t decimator_flag_bytes(int batch, long long max_samples) {
+  const long long rows = (octave_len(max_samples, 1) + dtc::kP - 1) / dtc::kP;
+  const long long tiles0 = (rows + dtc::kRowsOut - 1) / dtc::kRowsOut;
+  return sizeof(int) * (size_t)kDecStages * (size_t)(batch > 0 ? batch : 1) * (size_t)(tiles0 > 0 ? tiles0 : 1);
+}
+
+// the whole cascade: octave buffer i (1..6) of clip b lives at ws + b * ws_clip_stride + octave_offset(i)
+int launch_decimate_cascade_tc(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch,
+                               long long max_samples, long long wave_stride, float* ws, long long ws_clip_stride,
+                               int* flags, cudaStream_t st) {
+  if (batch == 0) return AST_OK;
+  if (!flags) return fail(AST_ERR_WORKSPACE, "the decimator needs its completion-flag region of the workspace");
   DecimateTcParams p;
-  p.in = in;
-  p.in_stride = in_stride;
-  p.out = out;
-  p.out_stride = out_stride;
+  p.wave = wave;
+  p.wave_stride = wave_stride;
+  p.ws = ws;
+  p.ws_clip_stride = ws_clip_stride;
+  for (int i = 0; i < kOctaves; ++i) p.oct_off[i] = i == 0 ? 0 : octave_offset(max_samples, i);
   p.lengths = lengths;
   p.max_samples = max_samples;
-  p.in_octave = in_octave;
   p.batch = batch;
-  const long long len_out = octave_len(max_samples, in_octave + 1);
-  const long long rows = (len_out + dtc::kP - 1) / dtc::kP;
-  p.tiles_per_clip = (int)((rows + dtc::kRowsOut - 1) / dtc::kRowsOut);
-  p.vec_ok = vec_ok;
+  long long total = 0;
+  for (int s = 0; s < kDecStages; ++s) {
+    const long long rows = (octave_len(max_samples, s + 1) + dtc::kP - 1) / dtc::kP;
+    p.tiles_per_clip[s] = (int)((rows + dtc::kRowsOut - 1) / dtc::kRowsOut);
+    p.tile_prefix[s] = (int)total;
+    total += (long long)p.tiles_per_clip[s] * batch;
+  }
+  if (total >= (1LL << 31)) return fail(AST_ERR_INVALID_ARG, "too many decimator tiles for one call");
+  p.tile_prefix[kDecStages] = (int)total;
+  p.vec_ok0 = (wave_stride % 4 == 0 || batch == 1) && (reinterpret_cast<uintptr_t>(wave) & 15) == 0;
+  p.flags = flags;
   p.strip_hi = plan->d_dec_strip_hi;
   p.strip_lo = plan->d_dec_strip_lo;
-  long long ctas = (long long)p.tiles_per_clip * batch;
-  if (ctas > plan->sm_count) ctas = plan->sm_count;  // persistent: one CTA per SM
-  if (ctas == 0) return AST_OK;
+  AST_CUDA_TRY(cudaMemsetAsync(flags, 0, decimator_flag_bytes(batch, max_samples), st));
+  long long ctas = total;
+  if (ctas > plan->sm_count) ctas = plan->sm_count;  // persistent and co-resident: one CTA per SM (tiles wait on each other)
   ProfileSpan span("decimate2_tc_kernel", st);
   AST_CUDA_TRY(launch_with_pdl(decimate2_tc_kernel, (unsigned)ctas, dtc::kThreads, dtc::kSmem, st, p));
   return AST_OK;
