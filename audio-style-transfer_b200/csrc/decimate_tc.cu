@@ -34,9 +34,10 @@
 // non-coherent path.
 //
 // One persistent CTA per SM, 13 warps:
-//   warps 0-7   producers: the NEXT tile's 64 KB of samples are loaded into registers (16 x LDG.128 per thread) while
-//               the current one is stored: raw -> A_hi (two whole tiles resident), x - trunc(x) -> A_lo (2-stage
-//               ring of 32-sample slices).  (cp.async was tried first: LDGSTS with a scattered destination costs
+//   warps 0-7   producers, two groups of four warps: group g stages slices 2 g, 2 g + 1 of each tile (raw -> A_hi, two
+//               whole tiles resident; x - trunc(x) -> A_lo, 2-stage ring of 32-sample slices), then loads the same
+//               slices of the NEXT tile into registers (16 x LDG.128 per thread) - fence.proxy.async waits for a
+//               thread's outstanding loads, so each group fences only when its prefetch has had ~2 us to land.  (cp.async was tried first: LDGSTS with a scattered destination costs
 //               one shared-memory wavefront per thread, 8x the LDG + conflict-free STS.128 path - ncu, profiles/.)
 //   warps 8-11  epilogue : TMEM -> registers, shifted sum by shuffles, stores (two accumulators, ping-pong)
 //   warp  12    MMA issue
@@ -71,10 +72,11 @@ constexpr int kEpilogueWarp0 = 8;
 constexpr int kMmaWarp = 12;
 constexpr int kThreads = 13 * 32;
 constexpr int kTmemCols = 512;                   // two 256-column accumulators
-constexpr int kChunksPerThread = kM * kSliceChunks / kProducers;  // 4
+constexpr int kProducerGroup = 128;               // producer threads per slice (two groups, two slices each)
+constexpr int kChunksPerThread = kM * kSliceChunks / kProducerGroup;  // 8
 constexpr int kEpiStride = kP + 4;               // floats per staged output row (conflict-free 16-byte accesses)
 constexpr int kEpiFloats = 4 * 32 * kEpiStride;  // one [32 rows][68] transpose buffer per epilogue warp
-constexpr size_t kSmem = sizeof(float) * (2 * kTileFloats + 2 * kSliceFloats + 2 * kStripFloats + kEpiFloats) + 128;
+constexpr size_t kSmem = sizeof(float) * (2 * kTileFloats + 2 * kSliceFloats + 2 * kStripFloats + kEpiFloats) + 192;
 }  // namespace dtc
 
 constexpr int kDecStages = kOctaves - 1;  // 6
@@ -152,9 +154,10 @@ __device__ __forceinline__ void dtc_dep_range(const DtcTile& t, int& k_lo, int& 
   k_hi = hi > lo ? (hi - 1) / (kRowsOut * kP) : k_lo - 1;
 }
 
-__device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
+// relaxed poll (an acquire load would invalidate L1 on every poll: CCTL.IVALL); the acquire fence follows success
+__device__ __forceinline__ int ld_relaxed_gpu(const int* ptr) {
   int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
   return v;
 }
 
@@ -164,8 +167,10 @@ __device__ __forceinline__ bool dtc_deps_ready(const DecimateTcParams& p, const 
   int k_lo, k_hi;
   dtc_dep_range(t, k_lo, k_hi);
   int ok = 1;
-  if (lane == 0)
-    for (int k = k_lo; k <= k_hi; ++k) ok &= ld_acquire_gpu(dtc_flag(p, t.stage - 1, t.clip, k)) >= 4 ? 1 : 0;
+  if (lane == 0) {
+    for (int k = k_lo; k <= k_hi; ++k) ok &= ld_relaxed_gpu(dtc_flag(p, t.stage - 1, t.clip, k)) >= 4 ? 1 : 0;
+    if (ok) __threadfence();  // acquire: the producers' stores (released by their fence + atomicAdd) are visible from here on
+  }
   ok = __shfl_sync(0xffffffffu, ok, 0);
   return ok != 0;
 }
@@ -203,18 +208,18 @@ __device__ __forceinline__ float4 dtc_load4(const float* x, int s, int len, bool
   return dtc_load4_partial(x, s, len);
 }
 
-// One 32-sample slice of a tile for this producer thread: chunk c = tid & 7 of rows (tid >> 3) + 32 i, i = 0..3
-// (row group i), read at sample 128 (row0 + 29 i + (tid >> 3)) - 192 + 32 s + 4 c.
-template <int S>
-__device__ __forceinline__ void dtc_load_slice(const DtcTile& t, int tid, float4 (&v)[16]) {
+// One 32-sample slice of a tile for a producer thread.  The producers work as two groups of 128 threads: group g
+// stages slices 2 g and 2 g + 1 of every tile, so a thread owns chunk c = tg & 7 of the eight rows
+// rho = (tg >> 3) + 16 i, i = 0..7 (tg = thread within the group), i.e. row group rho >> 5, lane row rho & 31,
+// read at sample 128 (row0 + 29 (rho >> 5) + (rho & 31)) - 192 + 32 s + 4 c.  J = 0 / 1: the group's first / second slice.
+template <int J>
+__device__ __forceinline__ void dtc_load_slice(const DtcTile& t, int tg, int s, float4 (&v)[16]) {
   using namespace dtc;
-  const int a0 = kRS * (t.row0 + (tid >> 3)) - kDecHalf + 32 * S + 4 * (tid & 7);
-  if (t.interior) {
+  const int a0 = kRS * (t.row0 + (tg >> 3)) - kDecHalf + 32 * s + 4 * (tg & 7);
 #pragma unroll
-    for (int i = 0; i < kChunksPerThread; ++i) v[4 * S + i] = ld_cg_f4(t.x + a0 + kRS * kGroupValid * i);
-  } else {
-#pragma unroll
-    for (int i = 0; i < kChunksPerThread; ++i) v[4 * S + i] = dtc_load4(t.x, a0 + kRS * kGroupValid * i, t.len_in, t.vec_ok);
+  for (int i = 0; i < kChunksPerThread; ++i) {
+    const int a = a0 + kRS * (kGroupValid * (i >> 1) + 16 * (i & 1));
+    v[kChunksPerThread * J + i] = t.interior ? ld_cg_f4(t.x + a) : dtc_load4(t.x, a, t.len_in, t.vec_ok);
   }
 }
 
@@ -227,12 +232,14 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
   float* t_lo = t_hi + kStripFloats;
   float* epi_buf = t_lo + kStripFloats;                  // [4 warps][32 rows][68] epilogue transpose
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + kEpiFloats);
-  uint64_t* l_full = bars;          // [2] producers -> MMA: slice staged (raw + lo written); 8 warp arrivals
-  uint64_t* l_empty = bars + 2;     // [2] MMA -> producers: the cross-term MMAs of the slice are done
-  uint64_t* h_empty = bars + 4;     // [2] MMA -> producers: all MMAs of the tile in this A_hi buffer are done
-  uint64_t* acc_full = bars + 6;    // [2] MMA -> epilogue
-  uint64_t* acc_empty = bars + 8;   // [2] epilogue -> MMA; 4 warp arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  // One barrier pair PER SLICE of a tile (not per ring stage): each is completed once per tile and waited once per
+  // tile by one party, so the two producer groups never skip a phase of a barrier (parity waits alias otherwise).
+  uint64_t* l_full = bars;          // [4] producers -> MMA: slice staged (raw + lo written); 4 warp arrivals (one group)
+  uint64_t* l_empty = bars + 4;     // [4] MMA -> producers: the cross-term MMAs of the slice are done (lo stage free)
+  uint64_t* h_empty = bars + 8;     // [2] MMA -> producers: all MMAs of the tile in this A_hi buffer are done
+  uint64_t* acc_full = bars + 10;   // [2] MMA -> epilogue
+  uint64_t* acc_empty = bars + 12;  // [2] epilogue -> MMA; 4 warp arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   pdl_launch_dependents();  // the next stage may start its prologue as soon as SMs free up
@@ -242,9 +249,11 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
   }
   if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, kTmemCols);
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      umma::mbar_init(l_full + i, kProducers / 32);
+    for (int i = 0; i < 4; ++i) {
+      umma::mbar_init(l_full + i, kProducerGroup / 32);
       umma::mbar_init(l_empty + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       umma::mbar_init(h_empty + i, 1);
       umma::mbar_init(acc_full + i, 1);
       umma::mbar_init(acc_empty + i, 4);
@@ -262,57 +271,49 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
 
   if (warp < kProducers / 32) {
     // ================================================================= producers
-    float4 v[16];  // one whole tile per CTA in registers: v[4 s + i] = slice s, row group i
-    const int slot0 = (tid & 7) * kRT + (tid >> 3);
+    // fence.proxy.async waits for every outstanding load of its thread, so a thread must not fence while the next
+    // tile's loads are in flight: group g stages slices 2 g, 2 g + 1 of tile n, then loads the same two slices of
+    // tile n + 1 and has the other group's two slices plus the hi*hi MMAs (~2 us) before its next fence.
+    const int grp = warp >> 2, tg = tid & (kProducerGroup - 1);
+    float4 v[16];  // v[8 j + i]: chunk i of the group's j-th slice
+    const int slot0 = (tg & 7) * kRT + (tg >> 3);
     DtcTile cur;
     if (tile >= 0 && tile < total) {
       cur = dtc_decode(p, tile);
       dtc_deps_wait(p, cur, lane);
-      dtc_load_slice<0>(cur, tid, v);
-      dtc_load_slice<1>(cur, tid, v);
-      dtc_load_slice<2>(cur, tid, v);
-      dtc_load_slice<3>(cur, tid, v);
+      dtc_load_slice<0>(cur, tg, 2 * grp, v);
+      dtc_load_slice<1>(cur, tg, 2 * grp + 1, v);
     }
     for (int n = 0; tile >= 0 && tile < total; ++n) {
       const int next = dtc_next_live(p, tile, total);
-      bool refill = false;  // the next tile's inputs exist already: load them slice by slice while this one is staged
-      if (next >= 0) {
-        cur = dtc_decode(p, next);
-        refill = dtc_deps_ready(p, cur, lane);
-      }
       // this A_hi buffer is free once the MMAs of tile n - 2 have completed
       umma::mbar_wait(h_empty + (n & 1), ((n >> 1) & 1) ^ 1);
       float4* hi_tile = reinterpret_cast<float4*>(a_hi + (n & 1) * kTileFloats);
-      auto stage = [&](auto s_tag) {
-        constexpr int S = decltype(s_tag)::value;
-        const int qs = 4 * n + S, st = qs & 1;
-        umma::mbar_wait(l_empty + st, ((qs >> 1) & 1) ^ 1);  // the cross MMAs that read this lo stage two slices ago are done
-        float4* hi = hi_tile + S * (kSliceFloats / 4);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int sl = 2 * grp + j;                 // slice of the tile
+        const int st = sl & 1;                      // lo ring stage
+        // the cross MMAs that read this lo stage two slices ago are done
+        if (sl >= 2) umma::mbar_wait(l_empty + sl - 2, n & 1);
+        else if (n > 0) umma::mbar_wait(l_empty + sl + 2, (n - 1) & 1);
+        float4* hi = hi_tile + sl * (kSliceFloats / 4);
         float4* lo = reinterpret_cast<float4*>(a_lo + st * kSliceFloats);
 #pragma unroll
         for (int i = 0; i < kChunksPerThread; ++i) {
           float4 h, l;
-          umma::split_tf32(v[4 * S + i], h, l);
-          hi[slot0 + 32 * i] = v[4 * S + i];   // raw: the tensor core truncates to TF32 itself
-          lo[slot0 + 32 * i] = l;
+          umma::split_tf32(v[kChunksPerThread * j + i], h, l);
+          hi[slot0 + 16 * i] = v[kChunksPerThread * j + i];   // raw: the tensor core truncates to TF32 itself
+          lo[slot0 + 16 * i] = l;
         }
         umma::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) umma::mbar_arrive(l_full + st);
-        // refill the freed registers with the next tile (measured: better than loading the whole tile after the
-        // last slice, although each fence.proxy.async then also waits for the previous slice's loads)
-        if (refill) dtc_load_slice<S>(cur, tid, v);
-      };
-      stage(std::integral_constant<int, 0>{});
-      stage(std::integral_constant<int, 1>{});
-      stage(std::integral_constant<int, 2>{});
-      stage(std::integral_constant<int, 3>{});
-      if (next >= 0 && !refill) {  // its producers were still running: wait for them now, then load the whole tile
-        dtc_deps_wait(p, cur, lane);
-        dtc_load_slice<0>(cur, tid, v);
-        dtc_load_slice<1>(cur, tid, v);
-        dtc_load_slice<2>(cur, tid, v);
-        dtc_load_slice<3>(cur, tid, v);
+        if (lane == 0) umma::mbar_arrive(l_full + sl);
+      }
+      if (next >= 0) {
+        cur = dtc_decode(p, next);
+        dtc_deps_wait(p, cur, lane);   // stage s + 1 tiles: the stage-s tiles that produce these samples have finished
+        dtc_load_slice<0>(cur, tg, 2 * grp, v);
+        dtc_load_slice<1>(cur, tg, 2 * grp + 1, v);
       }
       tile = next;
     }
@@ -329,8 +330,8 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
       umma::fence_after_thread_sync();
       // cross terms first (see the accuracy note in the header)
       for (int s = 0; s < kSlices; ++s) {
-        const int qs = 4 * n + s, st = qs & 1;
-        umma::mbar_wait(l_full + st, (qs >> 1) & 1);
+        const int st = s & 1;
+        umma::mbar_wait(l_full + s, n & 1);
         umma::fence_after_thread_sync();
         if (umma::elect_one_sync()) {
           const uint64_t da_hi = umma::smem_desc(hi_addr + (uint32_t)(s * kSliceFloats * 4), kRT * 16, 128);
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
             umma::mma_tf32(acc, da_lo + a_off, db_hi0 - b_off, idesc, (s | k) ? 1u : 0u);
             umma::mma_tf32(acc, da_hi + a_off, db_lo0 - b_off, idesc, 1u);
           }
-          umma::commit(l_empty + st);
+          umma::commit(l_empty + s);
         }
         __syncwarp();
       }
@@ -409,7 +410,6 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
         }
       }
       // publish: this warp's rows of the tile are in global memory (stages 0..4 feed another stage of this launch)
-      __threadfence();
       __syncwarp();  // also: the staging buffer is rewritten by the next tile
       if (lane == 0 && t.stage < kDecStages - 1) {
         __threadfence();
