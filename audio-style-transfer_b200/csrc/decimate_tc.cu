@@ -33,7 +33,7 @@
 // launches disappear.  Inputs produced by this launch are read with ld.global.cg (L2), never through L1 / the
 // non-coherent path.
 //
-// One persistent CTA per SM, 13 warps:
+// One persistent CTA per SM, 14 warps:
 //   warps 0-7   producers, two groups of four warps: group g stages slices 2 g, 2 g + 1 of each tile (raw -> A_hi, two
 //               whole tiles resident; x - trunc(x) -> A_lo, 2-stage ring of 32-sample slices), then loads the same
 //               slices of the NEXT tile into registers (16 x LDG.128 per thread) - fence.proxy.async waits for a
@@ -41,6 +41,8 @@
 //               one shared-memory wavefront per thread, 8x the LDG + conflict-free STS.128 path - ncu, profiles/.)
 //   warps 8-11  epilogue : TMEM -> registers, shifted sum by shuffles, stores (two accumulators, ping-pong)
 //   warp  12    MMA issue
+//   warp  13    publisher: completion counters of finished tiles
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -70,16 +72,26 @@ constexpr int kStripFloats = 2 * kStripRows * 4; // [chunk 2][row 320][4]
 constexpr int kProducers = 256;
 constexpr int kEpilogueWarp0 = 8;
 constexpr int kMmaWarp = 12;
-constexpr int kThreads = 13 * 32;
+constexpr int kPublishWarp = 13;                 // sets the tiles' completion counters, off the epilogue's critical path
+constexpr int kThreads = 14 * 32;
 constexpr int kTmemCols = 512;                   // two 256-column accumulators
 constexpr int kProducerGroup = 128;               // producer threads per slice (two groups, two slices each)
 constexpr int kChunksPerThread = kM * kSliceChunks / kProducerGroup;  // 8
 constexpr int kEpiStride = kP + 4;               // floats per staged output row (conflict-free 16-byte accesses)
 constexpr int kEpiFloats = 4 * 32 * kEpiStride;  // one [32 rows][68] transpose buffer per epilogue warp
-constexpr size_t kSmem = sizeof(float) * (2 * kTileFloats + 2 * kSliceFloats + 2 * kStripFloats + kEpiFloats) + 192;
+constexpr size_t kSmem = sizeof(float) * (2 * kTileFloats + 2 * kSliceFloats + 2 * kStripFloats + kEpiFloats) + 256;
 }  // namespace dtc
 
 constexpr int kDecStages = kOctaves - 1;  // 6
+
+#ifdef AST_TRACE
+// diagnostic build only (scratch/trace_dec.py): clock64 stamps of CTA 0's pipeline roles, per tile
+__device__ long long g_dec_trace[4][64][8];
+#define DTC_STAMP(role, idx, k) \
+  do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (idx) < 64) g_dec_trace[role][idx][k] = clock64(); } while (0)
+#else
+#define DTC_STAMP(role, idx, k) do {} while (0)
+#endif
 
 struct DecimateTcParams {
   const float* wave;       // octave 0: clip b at wave + b * wave_stride
@@ -96,6 +108,7 @@ struct DecimateTcParams {
   int* flags;                        // [stage][clip][tile of stage 0's count]: epilogue warps that finished the tile (4 = done)
   const float* strip_hi;   // [2][320][4] smem image of the Toeplitz strip (TF32-exact values)
   const float* strip_lo;
+  int debug;               // diagnostic bit mask (AST_DEC_DEBUG): 1 no epilogue shuffles / stores, 2 no producer loads, 4 no MMAs
 };
 
 struct DtcTile {
@@ -107,6 +120,7 @@ struct DtcTile {
   bool live;       // false: the tile lies past the clip's end (ragged batch)
   bool interior;   // every staged sample lies inside [0, len_in) and 16-byte loads are legal
   bool vec_ok;
+  int debug;
 };
 
 __device__ __forceinline__ DtcTile dtc_decode(const DecimateTcParams& p, int tile) {
@@ -128,6 +142,7 @@ __device__ __forceinline__ DtcTile dtc_decode(const DecimateTcParams& p, int til
   t.x = s == 0 ? p.wave + (long long)b * p.wave_stride : p.ws + (long long)b * p.ws_clip_stride + p.oct_off[s];
   t.y = p.ws + (long long)b * p.ws_clip_stride + p.oct_off[s + 1];
   t.vec_ok = s > 0 || p.vec_ok0;
+  t.debug = p.debug;
   const int first = kRS * t.row0 - kDecHalf;
   const int last = kRS * (t.row0 + kGroupValid * (kGroups - 1) + 31) - kDecHalf + kRS;  // one past the last staged sample
   t.interior = first >= 0 && last <= t.len_in && t.vec_ok;
@@ -216,6 +231,11 @@ template <int J>
 __device__ __forceinline__ void dtc_load_slice(const DtcTile& t, int tg, int s, float4 (&v)[16]) {
   using namespace dtc;
   const int a0 = kRS * (t.row0 + (tg >> 3)) - kDecHalf + 32 * s + 4 * (tg & 7);
+  if (t.debug & 2) {
+#pragma unroll
+    for (int i = 0; i < kChunksPerThread; ++i) v[kChunksPerThread * J + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < kChunksPerThread; ++i) {
     const int a = a0 + kRS * (kGroupValid * (i >> 1) + 16 * (i & 1));
@@ -240,6 +260,9 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
   uint64_t* acc_full = bars + 10;   // [2] MMA -> epilogue
   uint64_t* acc_empty = bars + 12;  // [2] epilogue -> MMA; 4 warp arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  // epilogue -> publisher: epilogue warps that have stored their rows, summed over all tiles (a monotonic counter
+  // cannot alias the way a lapped mbarrier parity would)
+  unsigned int* stored_count = reinterpret_cast<unsigned int*>(bars + 15);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   pdl_launch_dependents();  // the next stage may start its prologue as soon as SMs free up
@@ -258,6 +281,7 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
       umma::mbar_init(acc_full + i, 1);
       umma::mbar_init(acc_empty + i, 4);
     }
+    *stored_count = 0;
   }
   umma::fence_proxy_async_smem();
   umma::fence_before_thread_sync();
@@ -286,8 +310,10 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
     }
     for (int n = 0; tile >= 0 && tile < total; ++n) {
       const int next = dtc_next_live(p, tile, total);
+      if ((warp & 3) == 0) DTC_STAMP(grp, n, 0);
       // this A_hi buffer is free once the MMAs of tile n - 2 have completed
       umma::mbar_wait(h_empty + (n & 1), ((n >> 1) & 1) ^ 1);
+      if ((warp & 3) == 0) DTC_STAMP(grp, n, 1);
       float4* hi_tile = reinterpret_cast<float4*>(a_hi + (n & 1) * kTileFloats);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -296,6 +322,7 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
         // the cross MMAs that read this lo stage two slices ago are done
         if (sl >= 2) umma::mbar_wait(l_empty + sl - 2, n & 1);
         else if (n > 0) umma::mbar_wait(l_empty + sl + 2, (n - 1) & 1);
+        if ((warp & 3) == 0) DTC_STAMP(grp, n, 2 + 2 * j);
         float4* hi = hi_tile + sl * (kSliceFloats / 4);
         float4* lo = reinterpret_cast<float4*>(a_lo + st * kSliceFloats);
 #pragma unroll
@@ -308,12 +335,15 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
         umma::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(l_full + sl);
+        if ((warp & 3) == 0) DTC_STAMP(grp, n, 3 + 2 * j);
       }
       if (next >= 0) {
         cur = dtc_decode(p, next);
-        dtc_deps_wait(p, cur, lane);   // stage s + 1 tiles: the stage-s tiles that produce these samples have finished
+        dtc_deps_wait(p, cur, lane);
+        if ((warp & 3) == 0) DTC_STAMP(grp, n, 6);   // stage s + 1 tiles: the stage-s tiles that produce these samples have finished
         dtc_load_slice<0>(cur, tg, 2 * grp, v);
         dtc_load_slice<1>(cur, tg, 2 * grp + 1, v);
+        if ((warp & 3) == 0) DTC_STAMP(grp, n, 7);
       }
       tile = next;
     }
@@ -326,18 +356,22 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
       const int q = n & 1;
       const uint32_t acc = tmem_base + (uint32_t)(q * kN);
       const uint32_t hi_addr = umma::smem_u32(a_hi + q * kTileFloats);
+      DTC_STAMP(2, n, 0);
       umma::mbar_wait(acc_empty + q, ((n >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
       umma::fence_after_thread_sync();
+      DTC_STAMP(2, n, 1);
       // cross terms first (see the accuracy note in the header)
       for (int s = 0; s < kSlices; ++s) {
         const int st = s & 1;
         umma::mbar_wait(l_full + s, n & 1);
         umma::fence_after_thread_sync();
+        DTC_STAMP(2, n, 2 + s);
         if (umma::elect_one_sync()) {
           const uint64_t da_hi = umma::smem_desc(hi_addr + (uint32_t)(s * kSliceFloats * 4), kRT * 16, 128);
           const uint64_t da_lo = umma::smem_desc(umma::smem_u32(a_lo + st * kSliceFloats), kRT * 16, 128);
 #pragma unroll
           for (int k = 0; k < kKStepsPerSlice; ++k) {
+            if (p.debug & 4) break;
             const uint64_t a_off = (uint64_t)(2 * k * kRT);              // start-address field is in 16-byte units
             const uint64_t b_off = (uint64_t)(4 * (kKStepsPerSlice * s + k));  // strip row 60 - 4 gs
             umma::mma_tf32(acc, da_lo + a_off, db_hi0 - b_off, idesc, (s | k) ? 1u : 0u);
@@ -350,6 +384,7 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
       if (umma::elect_one_sync()) {
 #pragma unroll
         for (int gs = 0; gs < kSlices * kKStepsPerSlice; ++gs) {
+          if (p.debug & 4) break;
           const int s = gs >> 2, k = gs & 3;
           const uint64_t da_hi = umma::smem_desc(hi_addr + (uint32_t)(s * kSliceFloats * 4), kRT * 16, 128);
           umma::mma_tf32(acc, da_hi + (uint64_t)(2 * k * kRT), db_hi0 - (uint64_t)(4 * gs), idesc, 1u);
@@ -358,30 +393,40 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
         umma::commit(acc_full + q);   // ... and the accumulator is complete
       }
       __syncwarp();
+      DTC_STAMP(2, n, 6);
     }
-  } else {
+  } else if (warp < kPublishWarp) {
     // ================================================================= epilogue (warps 8-11)
     const int quad = warp - kEpilogueWarp0;  // == warp % 4: the TMEM lane quadrant this warp may read
     float* stg = epi_buf + quad * 32 * kEpiStride;
     for (int n = 0; tile >= 0 && tile < total; ++n, tile = dtc_next_live(p, tile, total)) {
       const int q = n & 1;
       const DtcTile t = dtc_decode(p, tile);
+      if (quad == 0) DTC_STAMP(3, n, 0);
       umma::mbar_wait(acc_full + q, (n >> 1) & 1);
       umma::fence_after_thread_sync();
+      if (quad == 0) DTC_STAMP(3, n, 1);
       const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(q * kN);
       // lane l of row group `quad` owns output row R = row0 + 29 quad + l (complete for l < 29)
 #pragma unroll
       for (int cq = 0; cq < kP / 16; ++cq) {
+        uint32_t r0[16], r1[16], r2[16], r3[16];
+        umma::tmem_ld_32x16_nowait(lane_base + 3 * kP + 16 * cq, r0);   // d = 0: this row
+        umma::tmem_ld_32x16_nowait(lane_base + 2 * kP + 16 * cq, r1);   // d = 1: wanted by the row above (lane - 1)
+        umma::tmem_ld_32x16_nowait(lane_base + 1 * kP + 16 * cq, r2);
+        umma::tmem_ld_32x16_nowait(lane_base + 16 * cq, r3);
+        umma::tmem_wait_ld();                                            // one TMEM round trip for the four loads
         float v0[16], v1[16], v2[16], v3[16];
-        umma::tmem_ld_32x16(lane_base + 3 * kP + 16 * cq, v0);   // d = 0: this row
-        umma::tmem_ld_32x16(lane_base + 2 * kP + 16 * cq, v1);   // d = 1: wanted by the row above (lane - 1)
-        umma::tmem_ld_32x16(lane_base + 1 * kP + 16 * cq, v2);
-        umma::tmem_ld_32x16(lane_base + 16 * cq, v3);
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          v0[c] = __uint_as_float(r0[c]), v1[c] = __uint_as_float(r1[c]), v2[c] = __uint_as_float(r2[c]), v3[c] = __uint_as_float(r3[c]);
         if (cq == kP / 16 - 1) {  // last TMEM read of the tile: hand the accumulator back
           umma::fence_before_thread_sync();
           __syncwarp();
           if (lane == 0) umma::mbar_arrive(acc_empty + q);
+          if (quad == 0) DTC_STAMP(3, n, 2);
         }
+        if (p.debug & 1) continue;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           const float s1 = __shfl_down_sync(0xffffffffu, v1[c], 1);
@@ -397,7 +442,7 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
       __syncwarp();
       // write-out along rows: 16 lanes cover one 256-byte row, so an instruction touches 4 lines instead of 29
       const int j_grp = (t.row0 + kGroupValid * quad) * kP;
-      for (int idx = lane; idx < kGroupValid * (kP / 4); idx += 32) {
+      for (int idx = lane; idx < kGroupValid * (kP / 4) && !(p.debug & 1); idx += 32) {
         const int r = idx >> 4, c4 = idx & 15;
         const int j = j_grp + r * kP + 4 * c4;
         const float4 val = *reinterpret_cast<const float4*>(stg + r * kEpiStride + 4 * c4);
@@ -411,10 +456,30 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
       }
       // publish: this warp's rows of the tile are in global memory (stages 0..4 feed another stage of this launch)
       __syncwarp();  // also: the staging buffer is rewritten by the next tile
-      if (lane == 0 && t.stage < kDecStages - 1) {
-        __threadfence();
-        atomicAdd(dtc_flag(p, t.stage, t.clip, t.k), 1);
+      if (quad == 0) DTC_STAMP(3, n, 3);
+      if (lane == 0) {   // release (CTA scope): the publisher warp makes it visible GPU-wide
+        __threadfence_block();
+        atomicAdd(stored_count, 1u);
       }
+    }
+  } else if (warp == kPublishWarp) {
+    // ================================================================= publisher
+    // Waiting for a tile's stores to be acknowledged (__threadfence) costs ~2000 cycles; done here it does not delay
+    // the epilogue's next tile.  stores (epilogue warps) -> mbarrier arrive / wait (CTA scope) -> fence (GPU scope,
+    // cumulative) -> counter: the consumers' acquire side is dtc_deps_ready.
+    for (int n = 0; tile >= 0 && tile < total; ++n, tile = dtc_next_live(p, tile, total)) {
+      const DtcTile t = dtc_decode(p, tile);
+      if (lane == 0) {
+        for (uint32_t spin = 0; *reinterpret_cast<volatile unsigned int*>(stored_count) < 4u * (unsigned)(n + 1); ++spin) {
+          __nanosleep(100);
+          if (spin > (1u << 26)) __trap();
+        }
+        if (t.stage < kDecStages - 1) {
+          __threadfence();
+          atomicAdd(dtc_flag(p, t.stage, t.clip, t.k), 4);
+        }
+      }
+      __syncwarp();
     }
   }
   umma::fence_before_thread_sync();
@@ -428,6 +493,12 @@ int decimate_init() {
 }
 
 int decimator_strip_floats() { return dtc::kStripFloats; }
+
+#ifdef AST_TRACE
+extern "C" int ast_debug_dec_trace(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, g_dec_trace, sizeof(long long) * 4 * 64 * 8);
+}
+#endif
 
 // host: the Toeplitz strip images T[jj][kk] = g[kk - 2 jj], jj = row - 252, as [chunk c][row][4] with kk = 4 c + e;
 // hi values are exactly representable in TF32, lo is the TF32-truncated residual of the double tap.
@@ -489,6 +560,10 @@ int launch_decimate_cascade_tc(const ast_plan* plan, const float* wave, const in
   p.flags = flags;
   p.strip_hi = plan->d_dec_strip_hi;
   p.strip_lo = plan->d_dec_strip_lo;
+  {
+    const char* env = getenv("AST_DEC_DEBUG");
+    p.debug = env ? atoi(env) : 0;
+  }
   AST_CUDA_TRY(cudaMemsetAsync(flags, 0, decimator_flag_bytes(batch, max_samples), st));
   long long ctas = total;
   if (ctas > plan->sm_count) ctas = plan->sm_count;  // persistent and co-resident: one CTA per SM (tiles wait on each other)
