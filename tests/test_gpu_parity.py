@@ -206,6 +206,26 @@ def test_config3_variable_length_batch(fe, piano_stats):
         assert np.abs(flat[i, :, :T_i, :513].cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("batch,n", [(1, 36608), (3, 70001), (150, 44100), (301, 40000)])
+def test_cqt_batch_shapes_exercise_the_decimator_tile_scheduler(fe, batch, n):
+    """The six decimator stages run as ONE launch whose tiles wait on each other through completion counters:
+    cover fewer tiles than CTAs, several tiles per CTA and more clips than SMs.  Every clip of the batch must equal
+    the same clip run alone (bit for bit: the arithmetic per tile does not depend on the schedule), and one of them
+    the oracle."""
+    base = np.stack([synth.clip("piano" if i % 2 == 0 else "violin", 200 + i, n) for i in range(min(batch, 5))])
+    gains = np.random.default_rng(batch).uniform(0.5, 1.5, batch).astype(np.float32)
+    wave = base[np.arange(batch) % len(base)] * gains[:, None]
+    out = fe.cqt(cuda(wave))
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (batch, 2, 1 + n // 256, 84)
+    for i in sorted({0, batch // 2, batch - 1}):
+        single = fe.cqt(cuda(wave[i])[None])
+        assert torch.equal(out[i], single[0]), i
+    V = oc.cqt(wave[batch - 1].astype(np.float64))
+    ref = np.stack([V.real.T, V.imag.T])
+    assert np.abs(out[batch - 1].cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
 def test_per_clip_statistics_and_batcher(fe, dl, piano_stats):
     import os
     from conftest import GOLDEN
