@@ -137,7 +137,7 @@ int ast_cqt_forward(const ast_plan* plan, const float* wave, const int32_t* leng
   rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, st);
   if (rc != AST_OK) return rc;
   OutSpec o = make_out(plan, out, AST_LAYOUT_FLAT, t_out, kFCqt, 0);  // 84-wide rows, CQT bin 0 at column 0
-  return launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, o, st);
+  return launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, use_tc_decimator() ? w.dec_flags : nullptr, o, st);
 }
 
 int ast_features_forward(const ast_plan* plan, const float* wave, const int32_t* lengths, int32_t batch,
@@ -182,23 +182,18 @@ int ast_features_forward(const ast_plan* plan, const float* wave, const int32_t*
     if (rc != AST_OK) return rc;
     rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, st);
     if (rc != AST_OK) return rc;
-    return launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, oq, st);
+    return launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, use_tc_decimator() ? w.dec_flags : nullptr, oq, st);
   }
-  // The STFT kernel lives on the FP32 pipes, the decimator + CQT projection on the tensor pipe, and they write
-  // disjoint columns of the same rows: fork the CQT branch onto the plan's side stream and join afterwards.
-  cudaEvent_t fork_ev, join_ev;
-  AST_CUDA_TRY(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
-  AST_CUDA_TRY(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming));
-  AST_CUDA_TRY(cudaEventRecord(fork_ev, st));
-  AST_CUDA_TRY(cudaStreamWaitEvent(plan->side_stream, fork_ev, 0));
-  rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, plan->side_stream);
-  if (rc == AST_OK) rc = launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, oq, plan->side_stream);
-  int rc2 = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st);
-  cudaEventRecord(join_ev, plan->side_stream);
-  cudaStreamWaitEvent(st, join_ev, 0);
-  cudaEventDestroy(fork_ev);  // released by the runtime once the recorded work has completed
-  cudaEventDestroy(join_ev);
-  return rc != AST_OK ? rc : rc2;
+  // One stream, three programmatic dependent launches: decimator cascade -> CQT projection (runs into the decimator's
+  // tail, block by block behind its completion counters) -> STFT (never waits: disjoint output columns; its small CTAs
+  // fill the SMs as the persistent CQT CTAs retire).  The memset inside launch_decimate_cascade is an ordinary stream
+  // operation, so nothing of this call starts before the previous call's kernels have finished.
+  rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, st);
+  if (rc == AST_OK)
+    rc = launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride,
+                    use_tc_decimator() ? w.dec_flags : nullptr, oq, st);
+  if (rc != AST_OK) return rc;
+  return launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st, 0, /*pdl=*/use_tc_decimator() && use_tc_cqt());
 }
 
 int ast_istft_forward(const ast_plan* plan, const float* spec, int32_t batch, int32_t dim1, int32_t f_in, int32_t layout,

@@ -57,10 +57,10 @@ struct ProfileSpan {
 // init) while the previous kernel of the stream is still draining; it must execute pdl_wait() before touching
 // anything the previous kernel reads or writes.  Off while profiling (events between launches would serialise).
 template <class Params>
-inline cudaError_t launch_with_pdl(void (*kernel)(Params), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+inline cudaError_t launch_with_pdl(void (*kernel)(Params), dim3 grid, unsigned block, size_t smem, cudaStream_t st,
                                    const Params& params) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
+  cfg.gridDim = grid;
   cfg.blockDim = dim3(block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -174,12 +174,13 @@ int launch_prep_stats(const float* mean, const float* std, float eps, int n, flo
 int launch_count_sections(const int32_t* lengths, int batch, long long max_samples, int layout, int dim1,
                           int window, int overlap, int32_t* n_out, cudaStream_t st);
 int launch_stft(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
-                long long wave_stride, const OutSpec& out, cudaStream_t st, int pad_zero = 0);
+                long long wave_stride, const OutSpec& out, cudaStream_t st, int pad_zero = 0, bool pdl = false);
 int launch_decimate_cascade(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch,
                             long long max_samples, long long wave_stride, float* ws, long long ws_clip_stride,
                             int* flags, cudaStream_t st);
 int launch_cqt(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
-               long long wave_stride, const float* ws, long long ws_clip_stride, const OutSpec& out, cudaStream_t st);
+               long long wave_stride, const float* ws, long long ws_clip_stride, const int* dec_flags, const OutSpec& out,
+               cudaStream_t st);
 int launch_istft(const ast_plan* plan, const float* spec, int batch, int dim1, int f_in, int layout, int window,
                  int overlap, int n_frames, float* wave_out, long long out_stride, cudaStream_t st);
 int launch_clip_stats(const float* feats, const int32_t* n_frames, int batch, int t_dim, int f_dim, double* clip_stats,
@@ -193,13 +194,17 @@ int cqt_tc_init();
 int cqt_tc_image_floats();
 void host_cqt_tc_images(const double* kmat_256x24, float* images);
 int launch_cqt_tc(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
-                  long long wave_stride, const float* ws, long long ws_clip_stride, const OutSpec& out, cudaStream_t st);
+                  long long wave_stride, const float* ws, long long ws_clip_stride, const int* dec_flags, const OutSpec& out,
+                  cudaStream_t st);
 void set_tc_cqt(int on);
 void set_overlap_streams(int on);
 bool use_tc_cqt();
 int decimator_strip_floats();
 void host_decimator_strip(const double* taps_scaled, float* strip_hi, float* strip_lo);  // decimator_strip_floats() each
 size_t decimator_flag_bytes(int batch, long long max_samples);
+int decimator_tile_outputs();                       // outputs per decimator tile (7424)
+int decimator_tiles_stage0(long long max_samples);  // tiles per clip of the first stage = row stride of the flag array
+bool use_tc_decimator();
 int launch_decimate_cascade_tc(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch,
                                long long max_samples, long long wave_stride, float* ws, long long ws_clip_stride,
                                int* flags, cudaStream_t st);

@@ -90,6 +90,9 @@ struct CqtTcParams {
   const float* bmat;   // [32 ks][2 c][64 j: hi then lo][4] smem image
   const float* scale;  // [7][12]
   bool vec_ok;
+  const int* flags;    // the decimator's per-tile completion counters ([stage][clip][tile], 4 = done) or nullptr
+  int flag_tiles0;     // tiles per clip of decimator stage 0 (row stride of the counters)
+  int dec_tile_outputs;
   int debug;   // diagnostic bit mask (AST_CQT_DEBUG): 1 no epilogue stores, 2 no producer loads, 4 no MMAs, 8 no L2 prefetch
   OutSpec out;
 };
@@ -104,14 +107,19 @@ struct BlockPlan {
   int n;
   bool vec_ok;
   bool interior;  // whole block inside [0, len) and 16-byte loads legal: no bounds checks
+  bool coherent;  // octave >= 1: written by the decimator launch this kernel overlaps with -> loads go through L2
+  const int* dep; // first completion counter this block waits for (nullptr: none), dep_n of them
+  int dep_n;
 };
 
+// Tiles are numbered octave by octave (octave, clip, tile in clip): octave 0 needs nothing from the decimator and
+// octave i only its stage i - 1, so the kernel can start while the decimator launch before it is still draining.
 __device__ __forceinline__ void decode_tile(const CqtTcParams& p, int tile, int& b, int& oct, int& t0) {
-  const int tiles_per_clip = p.tiles_per_clip_oct * kOctaves;
-  b = tile / tiles_per_clip;
-  const int rem = tile - b * tiles_per_clip;
-  oct = rem / p.tiles_per_clip_oct;
-  t0 = (rem - oct * p.tiles_per_clip_oct) * cqt_tc::kM;
+  const int tiles_per_oct = p.tiles_per_clip_oct * p.batch;
+  oct = tile / tiles_per_oct;
+  const int rem = tile - oct * tiles_per_oct;
+  b = rem / p.tiles_per_clip_oct;
+  t0 = (rem - b * p.tiles_per_clip_oct) * cqt_tc::kM;
 }
 
 __device__ __forceinline__ BlockPlan plan_block(const CqtTcParams& p, int b, int oct, int t0, int j, int tid) {
@@ -145,6 +153,18 @@ __device__ __forceinline__ BlockPlan plan_block(const CqtTcParams& p, int b, int
   }
   s.n = tid < n_chunks ? (n_chunks - tid + kProducers - 1) / kProducers : 0;
   s.interior = first >= 0 && last <= s.len && s.vec_ok;
+  s.coherent = oct > 0;
+  s.dep = nullptr;
+  s.dep_n = 0;
+  if (oct > 0 && p.flags) {
+    // decimator stage oct - 1 produced samples [lo, hi) of this octave in tiles lo / 7424 ... (hi - 1) / 7424
+    const int lo = first > 0 ? first : 0, hi = last < s.len ? last : s.len;
+    if (hi > lo) {
+      const int k_lo = lo / p.dec_tile_outputs, k_hi = (hi - 1) / p.dec_tile_outputs;
+      s.dep = p.flags + ((long long)(oct - 1) * p.batch + b) * p.flag_tiles0 + k_lo;
+      s.dep_n = k_hi - k_lo + 1;
+    }
+  }
   return s;
 }
 
@@ -223,7 +243,10 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
   __syncthreads();
   umma::fence_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();  // the octave signals come from the decimator launches just before this one
+  // Without completion counters (FMA decimator) wait for the whole previous launch; with them the kernel runs into the
+  // decimator's tail and every block waits only for the decimator tiles it reads (the counters are cleared by a
+  // memset BEFORE the decimator launch, which also orders this kernel after the previous call's kernels).
+  if (!p.flags) pdl_wait();
   const int total = p.tiles_per_clip_oct * kOctaves * p.batch;  // gridDim.x <= total
 
   if (warp < kProducers / 32) {
@@ -232,18 +255,46 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
     // outstanding load of the thread (measured: prefetching before the fence made the kernel 40 % slower), so the
     // latency hides behind the wait for the next stage to be released instead.
     float4 v[kStage];
+    // a block of octave >= 1 waits for the decimator tiles that produce its samples (one lane polls for the warp;
+    // bounded: a broken chain traps instead of hanging the GPU)
+    auto wait_deps = [&](const BlockPlan& sp) {
+      if (!sp.dep) return;
+      for (uint32_t spin = 0;; ++spin) {
+        int ok = 1;
+        if (lane == 0) {
+          for (int k = 0; k < sp.dep_n; ++k) {
+            int f;
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(sp.dep + k) : "memory");
+            ok &= f >= 4 ? 1 : 0;
+          }
+          if (ok) __threadfence();
+        }
+        if (__shfl_sync(0xffffffffu, ok, 0)) return;
+        __nanosleep(200);
+        if (spin > (1u << 24)) __trap();
+      }
+    };
     auto issue_loads = [&](const BlockPlan& sp) {
+      wait_deps(sp);
       if (p.debug & 2) {
 #pragma unroll
         for (int i = 0; i < kStage; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      } else if (sp.interior) {
+      } else if (sp.interior && !sp.coherent) {
 #pragma unroll
         for (int i = 0; i < kStage; ++i)
           if (i < sp.n) v[i] = __ldg(reinterpret_cast<const float4*>(sp.x + sp.s0 + i * sp.src_step));
-      } else {
+      } else if (sp.interior) {
+#pragma unroll
+        for (int i = 0; i < kStage; ++i)
+          if (i < sp.n) v[i] = umma::ld_cg_f4(sp.x + sp.s0 + i * sp.src_step);
+      } else if (!sp.coherent) {
 #pragma unroll
         for (int i = 0; i < kStage; ++i)
           if (i < sp.n) v[i] = umma::load4_zero_ext(sp.x, sp.s0 + i * sp.src_step, sp.len, sp.vec_ok);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kStage; ++i)
+          if (i < sp.n) v[i] = umma::load4_zero_ext_cg(sp.x, sp.s0 + i * sp.src_step, sp.len);
       }
     };
     int item = 0;
@@ -506,8 +557,12 @@ int cqt_tc_init() {
 }
 
 int launch_cqt_tc(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
-                  long long wave_stride, const float* ws, long long ws_clip_stride, const OutSpec& out, cudaStream_t st) {
+                  long long wave_stride, const float* ws, long long ws_clip_stride, const int* dec_flags, const OutSpec& out,
+                  cudaStream_t st) {
   CqtTcParams p;
+  p.flags = dec_flags;
+  p.flag_tiles0 = decimator_tiles_stage0(max_samples);
+  p.dec_tile_outputs = decimator_tile_outputs();
   p.wave = wave;
   p.wave_stride = wave_stride;
   p.ws = ws;
@@ -533,7 +588,7 @@ int launch_cqt_tc(const ast_plan* plan, const float* wave, const int32_t* length
   long long ctas = (long long)p.tiles_per_clip_oct * kOctaves * batch;
   if (ctas > plan->sm_count) ctas = plan->sm_count;  // persistent: one CTA per SM
   ProfileSpan span("cqt_tc_kernel", st);
-  AST_CUDA_TRY(launch_with_pdl(cqt_tc_kernel, (unsigned)ctas, cqt_tc::kThreads, cqt_tc::kSmem, st, p));
+  AST_CUDA_TRY(launch_with_pdl(cqt_tc_kernel, dim3((unsigned)ctas), cqt_tc::kThreads, cqt_tc::kSmem, st, p));
   return AST_OK;
 }
 

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(kDecThreads) decimate2_kernel(const DecimatePa
 
 static int g_use_tc_decimator = 1;
 void set_tc_decimator(int on) { g_use_tc_decimator = on; }
+bool use_tc_decimator() { return g_use_tc_decimator != 0; }
 
 int upload_decimator_taps(const float* taps_scaled) {
   float padded[kDecTaps + 7] = {0};

@@ -474,10 +474,8 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
           __nanosleep(100);
           if (spin > (1u << 26)) __trap();
         }
-        if (t.stage < kDecStages - 1) {
-          __threadfence();
-          atomicAdd(dtc_flag(p, t.stage, t.clip, t.k), 4);
-        }
+        __threadfence();   // every stage: the CQT projection that follows polls the same counters
+        atomicAdd(dtc_flag(p, t.stage, t.clip, t.k), 4);
       }
       __syncwarp();
     }
@@ -526,6 +524,12 @@ void host_decimator_strip(const double* taps_scaled, float* strip_hi, float* str
       }
 }
 
+int decimator_tile_outputs() { return dtc::kRowsOut * dtc::kP; }
+int decimator_tiles_stage0(long long max_samples) {
+  const long long rows = (octave_len(max_samples, 1) + dtc::kP - 1) / dtc::kP;
+  return (int)((rows + dtc::kRowsOut - 1) / dtc::kRowsOut);
+}
+
 size_t decimator_flag_bytes(int batch, long long max_samples) {
   const long long rows = (octave_len(max_samples, 1) + dtc::kP - 1) / dtc::kP;
   const long long tiles0 = (rows + dtc::kRowsOut - 1) / dtc::kRowsOut;
@@ -568,7 +572,7 @@ int launch_decimate_cascade_tc(const ast_plan* plan, const float* wave, const in
   long long ctas = total;
   if (ctas > plan->sm_count) ctas = plan->sm_count;  // persistent and co-resident: one CTA per SM (tiles wait on each other)
   ProfileSpan span("decimate2_tc_kernel", st);
-  AST_CUDA_TRY(launch_with_pdl(decimate2_tc_kernel, (unsigned)ctas, dtc::kThreads, dtc::kSmem, st, p));
+  AST_CUDA_TRY(launch_with_pdl(decimate2_tc_kernel, dim3((unsigned)ctas), dtc::kThreads, dtc::kSmem, st, p));
   return AST_OK;
 }
 

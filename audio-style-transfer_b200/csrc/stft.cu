@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(kStftThreads, 3) stft_kernel(const StftParams 
   extern __shared__ __align__(16) float2 smem[];
   float2* t1 = smem;
   float2* t2 = smem + kTw1Size;
+  pdl_launch_dependents();
   const int group = threadIdx.x >> 6, tid = threadIdx.x & 63;
   float2* buf1 = smem + kTw1Size + kTw2Size + group * (kBuf1Size + kBuf2Size);
   float2* buf2 = buf1 + kBuf1Size;
@@ -199,7 +200,7 @@ int stft_init() {
 }
 
 int launch_stft(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
-                long long wave_stride, const OutSpec& out, cudaStream_t st, int pad_zero) {
+                long long wave_stride, const OutSpec& out, cudaStream_t st, int pad_zero, bool pdl) {
   StftParams p;
   p.pad_zero = pad_zero;
   p.wave = wave;
@@ -224,8 +225,14 @@ int launch_stft(const ast_plan* plan, const float* wave, const int32_t* lengths,
   p.iters = (int)iters;
   dim3 grid((unsigned)((groups_per_clip + iters - 1) / iters), (unsigned)batch);
   ProfileSpan span("stft_kernel", st);
-  stft_kernel<<<grid, kStftThreads, kStftSmem, st>>>(p);
-  AST_LAUNCH_CHECK("stft_kernel");
+  if (pdl) {
+    // programmatic dependent of the CQT projection launched just before it on the same stream: the kernel never
+    // waits for it (disjoint output columns), so its CTAs fill the SMs as the persistent CQT CTAs retire
+    AST_CUDA_TRY(launch_with_pdl(stft_kernel, grid, kStftThreads, kStftSmem, st, p));
+  } else {
+    stft_kernel<<<grid, kStftThreads, kStftSmem, st>>>(p);
+    AST_LAUNCH_CHECK("stft_kernel");
+  }
   return AST_OK;
 }
 

@@ -194,5 +194,31 @@ __device__ __forceinline__ float4 load4_zero_ext(const float* __restrict__ x, in
   return load4_partial(x, s, len);
 }
 
+// the same through L2 only (ld.global.cg): for data another kernel / CTA may still be producing, where neither the
+// non-coherent path nor a stale L1 line is acceptable
+__device__ __forceinline__ float4 ld_cg_f4(const float* ptr) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_cg_f(const float* ptr) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(ptr) : "memory");
+  return v;
+}
+static __device__ __noinline__ float4 load4_partial_cg(const float* x, int s, int len) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s >= 0 && s < len) v.x = ld_cg_f(x + s);
+  if (s + 1 >= 0 && s + 1 < len) v.y = ld_cg_f(x + s + 1);
+  if (s + 2 >= 0 && s + 2 < len) v.z = ld_cg_f(x + s + 2);
+  if (s + 3 >= 0 && s + 3 < len) v.w = ld_cg_f(x + s + 3);
+  return v;
+}
+__device__ __forceinline__ float4 load4_zero_ext_cg(const float* x, int s, int len) {
+  if (s >= 0 && s + 3 < len) return ld_cg_f4(x + s);
+  if (s + 3 < 0 || s >= len) return make_float4(0.f, 0.f, 0.f, 0.f);
+  return load4_partial_cg(x, s, len);
+}
+
 }  // namespace umma
 }  // namespace ast
