@@ -72,33 +72,68 @@ __device__ __forceinline__ float2 load_bin(const FrameRows& f, long long plane, 
   return make_float2(re, im);
 }
 
-template <int N1>
-__device__ __forceinline__ void load_inputs(float2 (&v)[16], int tid, const FrameRows& fa, const FrameRows& fb,
-                                            long long plane, bool live_a, bool live_b) {
-  const int kk = ihalf_bin<N1>(tid);
-  v[N1] = ihalf_pack<N1>(tid, load_bin(fa, plane, kk, live_a), load_bin(fb, plane, kk, live_b));
-  if constexpr (N1 < 15) load_inputs<N1 + 1>(v, tid, fa, fb, plane, live_a, live_b);
+// The 16 inputs of a thread in two batches of eight: all loads of a batch (32, or 64 in an overlap region) are issued
+// before the first value is used, so a pair costs two global-memory round trips instead of sixteen (ncu: the kernel's
+// dominant stall was the long scoreboard on these loads, one round trip per input).
+template <int N0>
+__device__ __forceinline__ void load_inputs8(float2 (&v)[16], int tid, const FrameRows& fa, const FrameRows& fb,
+                                             long long plane, bool live_b) {
+  float are[8], aim[8], bre[8], bim[8];
+  int kk[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) kk[i] = (N0 + i) < 8 ? 64 * (N0 + i) + tid : 64 * (16 - (N0 + i)) - tid;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    are[i] = __ldg(fa.r0 + kk[i]);
+    aim[i] = __ldg(fa.r0 + plane + kk[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    bre[i] = live_b ? __ldg(fb.r0 + kk[i]) : 0.f;
+    bim[i] = live_b ? __ldg(fb.r0 + plane + kk[i]) : 0.f;
+  }
+  if (fa.r1) {  // ascending section order like the reference's += loop, then / count (= 2)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      are[i] = (__ldg(fa.r1 + kk[i]) + are[i]) * 0.5f;
+      aim[i] = (__ldg(fa.r1 + plane + kk[i]) + aim[i]) * 0.5f;
+    }
+  }
+  if (live_b && fb.r1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      bre[i] = (__ldg(fb.r1 + kk[i]) + bre[i]) * 0.5f;
+      bim[i] = (__ldg(fb.r1 + plane + kk[i]) + bim[i]) * 0.5f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float2 xa = make_float2(are[i], aim[i]), xb = make_float2(bre[i], bim[i]);
+    if ((N0 + i == 0 || N0 + i == 8) && tid == 0) xa.y = 0.f, xb.y = 0.f;  // self-conjugate bins 0 / 512
+    v[N0 + i] = (N0 + i) < 8 ? make_float2(xa.x - xb.y, -(xa.y + xb.x)) : make_float2(xa.x + xb.y, -(xb.x - xa.y));
+  }
 }
 
 // Register-resident overlap-add state of one thread: for each of its 4 columns, partial sums of the
 // five segments t .. t+4 touched by the frame pair (t, t+1).
 struct OlaEmit {
   float acc[4][5];
-  float wn[4][4];   // hann[q + 256 a] / 1024
+  const float* __restrict__ w;   // hann[n] / 1024; read through L1 (4 KB, always resident) instead of 16 registers per
+                                 // thread: the registers go to keeping the next pair's input loads in flight
   template <int S>
-  __device__ __forceinline__ void col(int /*q*/, const float2 (&z)[4]) {
+  __device__ __forceinline__ void col(int q, const float2 (&z)[4]) {
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      acc[S][a] = fmaf(z[a].x, wn[S][a], acc[S][a]);           // frame A (real lane)  -> segment t + a
-      acc[S][a + 1] = fmaf(-z[a].y, wn[S][a], acc[S][a + 1]);  // frame B (-imag lane) -> segment t + 1 + a
+      const float wn = __ldg(w + q + 256 * a);
+      acc[S][a] = fmaf(z[a].x, wn, acc[S][a]);           // frame A (real lane)  -> segment t + a
+      acc[S][a + 1] = fmaf(-z[a].y, wn, acc[S][a + 1]);  // frame B (-imag lane) -> segment t + 1 + a
     }
   }
 };
 
 // writes segments t and t + 1 (if they belong to this run) from acc[.][0] and acc[.][1]
-__device__ __forceinline__ void emit_segments(const IstftParams& p, const OlaEmit& ola, const float (&wsq)[4][4],
-                                              const float (&renv)[4], const int (&qs)[4], float* __restrict__ y, int t,
-                                              int g0, int g1) {
+__device__ __forceinline__ void emit_segments(const IstftParams& p, const OlaEmit& ola, const float (&renv)[4],
+                                              const int (&qs)[4], float* __restrict__ y, int t, int g0, int g1) {
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     const int g = t + c;
@@ -115,7 +150,10 @@ __device__ __forceinline__ void emit_segments(const IstftParams& p, const OlaEmi
           float env = 0.f;
 #pragma unroll
           for (int a = 3; a >= 0; --a)
-            if (g - a >= 0 && g - a < p.n_frames) env += wsq[s][a];
+            if (g - a >= 0 && g - a < p.n_frames) {
+              const float w = __ldg(p.hann_inv_n + qs[s] + 256 * a) * 1024.f;
+              env += w * w;
+            }
           yo[qs[s]] = ola.acc[s][c] / env;
         }
       }
@@ -123,7 +161,7 @@ __device__ __forceinline__ void emit_segments(const IstftParams& p, const OlaEmi
   }
 }
 
-__global__ void __launch_bounds__(kIstftThreads, 12) istft_kernel(const IstftParams p) {
+__global__ void __launch_bounds__(kIstftThreads, 10) istft_kernel(const IstftParams p) {
   extern __shared__ __align__(16) float2 smem[];
   const float2* __restrict__ t1 = p.t1;  // 10 KB of twiddles stay L1-resident; shared memory is kept for the
   const float2* __restrict__ t2 = p.t2;  // exchange buffers so that 12 CTAs fit on an SM
@@ -141,18 +179,18 @@ __global__ void __launch_bounds__(kIstftThreads, 12) istft_kernel(const IstftPar
   const int qs[4] = {first ? 0 : tid, first ? 128 : 256 - tid, first ? 64 : 128 - tid, first ? 192 : 128 + tid};
 
   OlaEmit ola;
-  float wsq[4][4];
-#pragma unroll
-  for (int s = 0; s < 4; ++s)
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const float w = __ldg(p.hann_inv_n + qs[s] + 256 * a);
-      ola.wn[s][a] = w;
-      wsq[s][a] = (w * 1024.f) * (w * 1024.f);
-    }
+  ola.w = p.hann_inv_n;
   float renv[4];  // 1 / (w^2 summed over four frames, frame-ascending), the interior envelope
 #pragma unroll
-  for (int s = 0; s < 4; ++s) renv[s] = 1.0f / (((wsq[s][3] + wsq[s][2]) + wsq[s][1]) + wsq[s][0]);
+  for (int s = 0; s < 4; ++s) {
+    float wsq[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const float w = __ldg(p.hann_inv_n + qs[s] + 256 * a) * 1024.f;
+      wsq[a] = w * w;
+    }
+    renv[s] = 1.0f / (((wsq[3] + wsq[2]) + wsq[1]) + wsq[0]);
+  }
 #pragma unroll
   for (int s = 0; s < 4; ++s)
 #pragma unroll
@@ -167,7 +205,8 @@ __global__ void __launch_bounds__(kIstftThreads, 12) istft_kernel(const IstftPar
       const FrameRows fa = merged_rows(p, clip, t);
       const FrameRows fb = live_b ? merged_rows(p, clip, t + 1) : fa;
       float2 v[16];
-      load_inputs<0>(v, tid, fa, fb, p.plane, live_a, live_b);
+      load_inputs8<0>(v, tid, fa, fb, p.plane, live_b);
+      load_inputs8<8>(v, tid, fa, fb, p.plane, live_b);
       fft1024_stage1(v, tid, t1, buf1);
     }
     __syncthreads();
@@ -175,7 +214,7 @@ __global__ void __launch_bounds__(kIstftThreads, 12) istft_kernel(const IstftPar
     __syncthreads();
     fft1024_stage3_columns(tid, buf2, ola);
     // segments t and t + 1 are complete now (no later frame reaches them)
-    emit_segments(p, ola, wsq, renv, qs, y, t, g0, g1);
+    emit_segments(p, ola, renv, qs, y, t, g0, g1);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       ola.acc[s][0] = ola.acc[s][2];
@@ -187,7 +226,7 @@ __global__ void __launch_bounds__(kIstftThreads, 12) istft_kernel(const IstftPar
     t_next = t + 2;
   }
   // when the clip ends on an even frame count the last segment (g = n_frames) is still pending
-  emit_segments(p, ola, wsq, renv, qs, y, t_next, g0, g1);
+  emit_segments(p, ola, renv, qs, y, t_next, g0, g1);
 }
 
 static int g_istft_ctas_per_sm = 12;
