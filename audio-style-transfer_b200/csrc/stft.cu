@@ -10,6 +10,8 @@
 // per-clip bookkeeping is CTA-uniform.  Interior frames take a check-free load path; rows whose
 // destinations are all live take a select-free store path.  Shared memory per CTA: 10 KB twiddle
 // tables + 4 x (8320 B + 8192 B) exchange buffers = 76 288 B.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ast {
@@ -29,6 +31,7 @@ struct StftParams {
   const float2* t2;
   const float* hann;
   int overlap;
+  int debug;            // diagnostic (AST_STFT_DEBUG): 1 stores suppressed (only k == 1000000 would store)
   int pad_zero;         // 0: reflect padding (torch.stft, get_STFT); 1: zero padding (librosa.stft default, mse_spectrogram)
   OutSpec out;
 };
@@ -134,6 +137,7 @@ __global__ void __launch_bounds__(kStftThreads, 3) stft_kernel(const StftParams 
     st1 = st0 + p.out.f_stats;
   }
   const long long plane = (long long)(p.out.layout == AST_LAYOUT_FLAT ? p.out.dim1 : p.out.window) * p.out.f_row;
+  const bool no_store = p.debug & 1;
   __syncthreads();
 
   for (int it = 0; it < p.iters; ++it) {
@@ -173,6 +177,7 @@ __global__ void __launch_bounds__(kStftThreads, 3) stft_kernel(const StftParams 
       bool la0, la1, lb0 = false, lb1 = false;
       frame_rows(p.out, b, ta, frames_b, sections_b, a0, a1, la0, la1);
       if (ta + 1 < p.slots) frame_rows(p.out, b, ta + 1, frames_b, sections_b, b0, b1, lb0, lb1);
+      if (no_store) a0 = a1 = b0 = b1 = nullptr, la0 = false;  // diagnostic: all stores predicated off (not-all-live path)
       const bool all_live = la0 && (la1 || !a1) && (lb0 || !b0) && (lb1 || !b1);
       if (any_live && all_live) {
         StftEmit<true> emit{a0, a1, b0, b1, true, true, true, true, plane, st0, st1};
@@ -203,6 +208,10 @@ int launch_stft(const ast_plan* plan, const float* wave, const int32_t* lengths,
                 long long wave_stride, const OutSpec& out, cudaStream_t st, int pad_zero, bool pdl) {
   StftParams p;
   p.pad_zero = pad_zero;
+  {
+    const char* env = getenv("AST_STFT_DEBUG");
+    p.debug = env ? atoi(env) : 0;
+  }
   p.wave = wave;
   p.lengths = lengths;
   p.max_samples = max_samples;
