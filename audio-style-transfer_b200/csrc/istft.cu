@@ -82,6 +82,9 @@ __device__ __forceinline__ void load_inputs8(float2 (&v)[16], int tid, const Fra
   int kk[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) kk[i] = (N0 + i) < 8 ? 64 * (N0 + i) + tid : 64 * (16 - (N0 + i)) - tid;
+  // the second section row of an overlap frame is loaded in the same batch (predicated off elsewhere), not after it
+  const bool dup_a = fa.r1 != nullptr, dup_b = live_b && fb.r1 != nullptr;
+  float are1[8], aim1[8], bre1[8], bim1[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     are[i] = __ldg(fa.r0 + kk[i]);
@@ -92,18 +95,28 @@ __device__ __forceinline__ void load_inputs8(float2 (&v)[16], int tid, const Fra
     bre[i] = live_b ? __ldg(fb.r0 + kk[i]) : 0.f;
     bim[i] = live_b ? __ldg(fb.r0 + plane + kk[i]) : 0.f;
   }
-  if (fa.r1) {  // ascending section order like the reference's += loop, then / count (= 2)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    are1[i] = dup_a ? __ldg(fa.r1 + kk[i]) : 0.f;
+    aim1[i] = dup_a ? __ldg(fa.r1 + plane + kk[i]) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    bre1[i] = dup_b ? __ldg(fb.r1 + kk[i]) : 0.f;
+    bim1[i] = dup_b ? __ldg(fb.r1 + plane + kk[i]) : 0.f;
+  }
+  if (dup_a) {  // ascending section order like the reference's += loop, then / count (= 2)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      are[i] = (__ldg(fa.r1 + kk[i]) + are[i]) * 0.5f;
-      aim[i] = (__ldg(fa.r1 + plane + kk[i]) + aim[i]) * 0.5f;
+      are[i] = (are1[i] + are[i]) * 0.5f;
+      aim[i] = (aim1[i] + aim[i]) * 0.5f;
     }
   }
-  if (live_b && fb.r1) {
+  if (dup_b) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      bre[i] = (__ldg(fb.r1 + kk[i]) + bre[i]) * 0.5f;
-      bim[i] = (__ldg(fb.r1 + plane + kk[i]) + bim[i]) * 0.5f;
+      bre[i] = (bre1[i] + bre[i]) * 0.5f;
+      bim[i] = (bim1[i] + bim[i]) * 0.5f;
     }
   }
 #pragma unroll
