@@ -205,6 +205,8 @@ size_t decimator_flag_bytes(int batch, long long max_samples);
 int decimator_tile_outputs();                       // outputs per decimator tile (7424)
 int decimator_tiles_stage0(long long max_samples);  // tiles per clip of the first stage = row stride of the flag array
 bool use_tc_decimator();
+long long decimator_stage_done_offset(int batch, long long max_samples);  // ints from the flags to the per-stage counters
+int decimator_tiles_of_stage(long long max_samples, int stage);            // tiles per clip of a stage
 int launch_decimate_cascade_tc(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch,
                                long long max_samples, long long wave_stride, float* ws, long long ws_clip_stride,
                                int* flags, cudaStream_t st);

@@ -92,6 +92,8 @@ struct CqtTcParams {
   bool vec_ok;
   const int* flags;    // the decimator's per-tile completion counters ([stage][clip][tile], 4 = done) or nullptr
   int flag_tiles0;     // tiles per clip of decimator stage 0 (row stride of the counters)
+  const int* stage_done;          // finished-tile counter per decimator stage
+  int stage_tiles[kOctaves - 1];  // tiles of each stage (all clips): stage_done[s] == stage_tiles[s] <=> stage complete
   int dec_tile_outputs;
   int debug;   // diagnostic bit mask (AST_CQT_DEBUG): 1 no epilogue stores, 2 no producer loads, 4 no MMAs, 8 no L2 prefetch
   OutSpec out;
@@ -110,6 +112,7 @@ struct BlockPlan {
   bool coherent;  // octave >= 1: written by the decimator launch this kernel overlaps with -> loads go through L2
   const int* dep; // first completion counter this block waits for (nullptr: none), dep_n of them
   int dep_n;
+  int dep_stage;
 };
 
 // Tiles are numbered octave by octave (octave, clip, tile in clip): octave 0 needs nothing from the decimator and
@@ -163,6 +166,7 @@ __device__ __forceinline__ BlockPlan plan_block(const CqtTcParams& p, int b, int
       const int k_lo = lo / p.dec_tile_outputs, k_hi = (hi - 1) / p.dec_tile_outputs;
       s.dep = p.flags + ((long long)(oct - 1) * p.batch + b) * p.flag_tiles0 + k_lo;
       s.dep_n = k_hi - k_lo + 1;
+      s.dep_stage = oct - 1;
     }
   }
   return s;
@@ -257,8 +261,22 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
     float4 v[kStage];
     // a block of octave >= 1 waits for the decimator tiles that produce its samples (one lane polls for the warp;
     // bounded: a broken chain traps instead of hanging the GPU)
+    unsigned stages_complete = 0;  // bit s: decimator stage s has been seen complete (warp-uniform)
     auto wait_deps = [&](const BlockPlan& sp) {
-      if (!sp.dep) return;
+      if (!sp.dep || ((stages_complete >> sp.dep_stage) & 1)) return;
+      {  // one look at the stage's finished-tile counter: once it is full, no block of this octave polls again
+        int full = 0;
+        if (lane == 0) {
+          int f;
+          asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(p.stage_done + sp.dep_stage) : "memory");
+          full = f >= p.stage_tiles[sp.dep_stage] ? 1 : 0;
+          if (full) __threadfence();
+        }
+        if (__shfl_sync(0xffffffffu, full, 0)) {
+          stages_complete |= 1u << sp.dep_stage;
+          return;
+        }
+      }
       for (uint32_t spin = 0;; ++spin) {
         int ok = 1;
         if (lane == 0) {
@@ -562,6 +580,8 @@ int launch_cqt_tc(const ast_plan* plan, const float* wave, const int32_t* length
   CqtTcParams p;
   p.flags = dec_flags;
   p.flag_tiles0 = decimator_tiles_stage0(max_samples);
+  p.stage_done = dec_flags ? dec_flags + decimator_stage_done_offset(batch, max_samples) : nullptr;
+  for (int s = 0; s < kOctaves - 1; ++s) p.stage_tiles[s] = decimator_tiles_of_stage(max_samples, s) * batch;
   p.dec_tile_outputs = decimator_tile_outputs();
   p.wave = wave;
   p.wave_stride = wave_stride;

@@ -467,15 +467,23 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
     // Waiting for a tile's stores to be acknowledged (__threadfence) costs ~2000 cycles; done here it does not delay
     // the epilogue's next tile.  stores (epilogue warps) -> mbarrier arrive / wait (CTA scope) -> fence (GPU scope,
     // cumulative) -> counter: the consumers' acquire side is dtc_deps_ready.
-    for (int n = 0; tile >= 0 && tile < total; ++n, tile = dtc_next_live(p, tile, total)) {
-      const DtcTile t = dtc_decode(p, tile);
+    // Every tile of this CTA's list, live or not, also bumps its stage's finished-tile counter: a consumer that has
+    // seen a stage complete (counter == tiles of the stage) stops polling per-tile counters for it.
+    int* stage_done = p.flags + (long long)kDecStages * p.batch * p.tiles_per_clip[0];
+    int n = 0;
+    for (int g = blockIdx.x; g < total; g += gridDim.x) {
+      const DtcTile t = dtc_decode(p, g);
       if (lane == 0) {
-        for (uint32_t spin = 0; *reinterpret_cast<volatile unsigned int*>(stored_count) < 4u * (unsigned)(n + 1); ++spin) {
-          __nanosleep(100);
-          if (spin > (1u << 26)) __trap();
+        if (t.live) {
+          ++n;
+          for (uint32_t spin = 0; *reinterpret_cast<volatile unsigned int*>(stored_count) < 4u * (unsigned)n; ++spin) {
+            __nanosleep(100);
+            if (spin > (1u << 26)) __trap();
+          }
+          __threadfence();   // every stage: the CQT projection that follows polls the same counters
+          atomicAdd(dtc_flag(p, t.stage, t.clip, t.k), 4);
         }
-        __threadfence();   // every stage: the CQT projection that follows polls the same counters
-        atomicAdd(dtc_flag(p, t.stage, t.clip, t.k), 4);
+        atomicAdd(stage_done + t.stage, 1);
       }
       __syncwarp();
     }
@@ -530,10 +538,19 @@ int decimator_tiles_stage0(long long max_samples) {
   return (int)((rows + dtc::kRowsOut - 1) / dtc::kRowsOut);
 }
 
+int decimator_tiles_of_stage(long long max_samples, int stage) {
+  const long long rows = (octave_len(max_samples, stage + 1) + dtc::kP - 1) / dtc::kP;
+  return (int)((rows + dtc::kRowsOut - 1) / dtc::kRowsOut);
+}
+
 size_t decimator_flag_bytes(int batch, long long max_samples) {
   const long long rows = (octave_len(max_samples, 1) + dtc::kP - 1) / dtc::kP;
   const long long tiles0 = (rows + dtc::kRowsOut - 1) / dtc::kRowsOut;
-  return sizeof(int) * (size_t)kDecStages * (size_t)(batch > 0 ? batch : 1) * (size_t)(tiles0 > 0 ? tiles0 : 1);
+  // per-tile counters [stage][clip][tile], then one finished-tile counter per stage
+  return sizeof(int) * ((size_t)kDecStages * (size_t)(batch > 0 ? batch : 1) * (size_t)(tiles0 > 0 ? tiles0 : 1) + kDecStages);
+}
+long long decimator_stage_done_offset(int batch, long long max_samples) {
+  return (long long)kDecStages * (batch > 0 ? batch : 1) * decimator_tiles_stage0(max_samples);
 }
 
 // the whole cascade: octave buffer i (1..6) of clip b lives at ws + b * ws_clip_stride + octave_offset(i)
