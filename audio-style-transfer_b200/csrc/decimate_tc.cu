@@ -177,8 +177,20 @@ __device__ __forceinline__ int ld_relaxed_gpu(const int* ptr) {
 }
 
 // true when every producer tile of t has been completed by its four epilogue warps (one lane polls for the warp)
-__device__ __forceinline__ bool dtc_deps_ready(const DecimateTcParams& p, const DtcTile& t, int lane) {
-  if (t.stage == 0) return true;
+__device__ __forceinline__ bool dtc_deps_ready(const DecimateTcParams& p, const DtcTile& t, int lane, unsigned& stages_complete) {
+  if (t.stage == 0 || ((stages_complete >> (t.stage - 1)) & 1)) return true;
+  {  // the whole previous stage finished? then nothing of this stage needs to poll (or fence) again
+    int full = 0;
+    if (lane == 0) {
+      const int* stage_done = p.flags + (long long)kDecStages * p.batch * p.tiles_per_clip[0];
+      full = ld_relaxed_gpu(stage_done + t.stage - 1) >= p.tiles_per_clip[t.stage - 1] * p.batch ? 1 : 0;
+      if (full) __threadfence();
+    }
+    if (__shfl_sync(0xffffffffu, full, 0)) {
+      stages_complete |= 1u << (t.stage - 1);
+      return true;
+    }
+  }
   int k_lo, k_hi;
   dtc_dep_range(t, k_lo, k_hi);
   int ok = 1;
@@ -191,8 +203,8 @@ __device__ __forceinline__ bool dtc_deps_ready(const DecimateTcParams& p, const 
 }
 
 // Bounded wait: a broken dependency chain traps (kernel error) instead of hanging the GPU.
-__device__ __forceinline__ void dtc_deps_wait(const DecimateTcParams& p, const DtcTile& t, int lane) {
-  for (uint32_t spin = 0; !dtc_deps_ready(p, t, lane); ++spin) {
+__device__ __forceinline__ void dtc_deps_wait(const DecimateTcParams& p, const DtcTile& t, int lane, unsigned& stages_complete) {
+  for (uint32_t spin = 0; !dtc_deps_ready(p, t, lane, stages_complete); ++spin) {
     __nanosleep(200);
     if (spin > (1u << 24)) __trap();
   }
@@ -300,11 +312,12 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
     // tile n + 1 and has the other group's two slices plus the hi*hi MMAs (~2 us) before its next fence.
     const int grp = warp >> 2, tg = tid & (kProducerGroup - 1);
     float4 v[16];  // v[8 j + i]: chunk i of the group's j-th slice
+    unsigned stages_complete = 0;  // bit s: stage s has been seen complete
     const int slot0 = (tg & 7) * kRT + (tg >> 3);
     DtcTile cur;
     if (tile >= 0 && tile < total) {
       cur = dtc_decode(p, tile);
-      dtc_deps_wait(p, cur, lane);
+      dtc_deps_wait(p, cur, lane, stages_complete);
       dtc_load_slice<0>(cur, tg, 2 * grp, v);
       dtc_load_slice<1>(cur, tg, 2 * grp + 1, v);
     }
@@ -339,7 +352,7 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
       }
       if (next >= 0) {
         cur = dtc_decode(p, next);
-        dtc_deps_wait(p, cur, lane);
+        dtc_deps_wait(p, cur, lane, stages_complete);
         if ((warp & 3) == 0) DTC_STAMP(grp, n, 6);   // stage s + 1 tiles: the stage-s tiles that produce these samples have finished
         dtc_load_slice<0>(cur, tg, 2 * grp, v);
         dtc_load_slice<1>(cur, tg, 2 * grp + 1, v);
