@@ -10,9 +10,10 @@
 // smem[e][R] (e = chunk within a row stride of m = h_i / 4 chunks, R = row), and in the no-swizzle K-major
 // layout (rows 16 B apart) frame r's chunk c' = m d + e sits at row r + d: a window shift is +16 d bytes on the
 // descriptor start address.
-//   octave 0 (m = 64): four blocks (chunk columns 16 j .. 16 j + 15), 8 K-steps each, no shift needed
-//   octave 1 (m = 32): two blocks of 129 rows, each serving the K-steps of d = 0 and d = 1
-//   octave 2 (m = 16): one block of 131 rows, d = 0..3
+// A block is eight chunk columns (32 samples of every row it holds):
+//   octave 0 (m = 64): eight blocks (chunk columns 8 j .. 8 j + 7), 4 K-steps each, no shift needed
+//   octave 1 (m = 32): four blocks of 129 rows, each serving the K-steps of d = 0 and d = 1
+//   octave 2 (m = 16): two blocks of 131 rows, d = 0..3
 //   octaves 3-6 (m = 8, 4, 2, 1): one block = one contiguous run of the signal, 135 .. 191 rows
 // so a clip's seven octaves cost 1.76 MB of staging instead of the 3.5 MB of a per-pass slice scheme (the kernel
 // is bound by the shared-memory / LSU data path, not by the tensor pipe: profiles/).
@@ -26,7 +27,10 @@
 // (x - mean) * rstd, and stores to the flat / section layout (columns 513..596).
 //
 // One persistent CTA per SM, 16 warps:
-//   warps 0-6   producers: global -> registers -> hi / lo split -> shared A block (2 stages, mbarrier full / empty)
+//   warps 0-5   producers: global -> registers -> hi / lo split -> shared A block (4-stage ring, mbarrier full / empty);
+//               two groups of three warps take alternate blocks: fence.proxy.async waits for a thread's outstanding
+//               loads, so a group issues the loads of its NEXT block right after publishing one and does not fence
+//               again until the other group's block has gone by
 //   warps 8-15  epilogue : TMEM -> registers -> shared transpose -> global; two groups of four warps (one TMEM lane
 //               quadrant each) take alternate tiles, i.e. one accumulator set each - the epilogue, not the tensor
 //               pipe, is the longest stage of a tile (scratch/trace_cqt.py, scratch/dbg_cqt.sh)
@@ -43,22 +47,25 @@ namespace cqt_tc {
 constexpr int kM = 128;                 // frames per tile
 constexpr int kN = 32;                  // 24 outputs padded to 32
 constexpr int kKSteps = 32;             // 256-sample window / 8
-constexpr int kProducers = 224;         // threads of warps 0-6 (a multiple of 16 and of every m < 16)
-constexpr int kMmaWarp = 7;
+constexpr int kGroupThreads = 96;       // producer group: three warps (a multiple of 8 and of every m < 8)
+constexpr int kProducerWarps = 6;       // two groups, warps 0-2 and 3-5, alternate blocks
+constexpr int kMmaWarp = 7;             // (warp 6 idles: 16 warps keep four per scheduler, i.e. 128 registers per thread)
 constexpr int kEpilogueWarp0 = 8;       // warps 8-11: even tiles, warps 12-15: odd tiles
 constexpr int kThreads = 16 * 32;       // 4 warps per scheduler: 128 registers per thread
-constexpr int kMaxBlockChunks = 16 * 131;                 // octave 2: the largest block, 2096 chunks
-constexpr int kAFloats = kMaxBlockChunks * 4;             // 8384 floats = 33 536 B per split term
+constexpr int kBlockCols = 8;                             // chunk columns per block (32 samples of every row)
+constexpr int kStages = 4;                                // ring of staged blocks
+constexpr int kMaxBlockChunks = 8 * 135;                  // octave 3: the largest block, 1080 chunks
+constexpr int kAFloats = kMaxBlockChunks * 4;             // 4320 floats = 17 280 B per split term
 constexpr int kStageFloats = 2 * kAFloats;                // hi + lo
 constexpr int kBStepFloats = 2 * 2 * kN * 4;              // one K-step of [B_hi | B_lo]: [c 2][j 64][4] = 512 floats
 constexpr int kBFloats = kKSteps * kBStepFloats;          // 16384 floats = 64 KB
 constexpr int kMainAcc = 2;
 constexpr int kSetCols = kMainAcc * 2 * kN;               // 128 TMEM columns per accumulator set
 constexpr int kTmemCols = 256;
-constexpr int kStage = (kMaxBlockChunks + kProducers - 1) / kProducers;  // 10 chunks per producer thread per block at most
+constexpr int kStage = (kMaxBlockChunks + kGroupThreads - 1) / kGroupThreads;  // 12 chunks per producer thread per block at most
 constexpr int kEpiStride = 25;            // floats per staged row (24 values + 1: conflict-free row-per-lane writes)
 constexpr int kEpiFloats = 8 * 32 * kEpiStride;  // one [32 rows][25] transpose buffer per epilogue warp
-constexpr size_t kSmem = sizeof(float) * (2 * kStageFloats + kBFloats + kEpiFloats) + 128;
+constexpr size_t kSmem = sizeof(float) * (kStages * kStageFloats + kBFloats + kEpiFloats) + 128;
 
 // rows per chunk column of an octave's blocks: 128 frames + window / hop - 1 shifts, rounded up to an odd
 // number (conflict-free transposed 16-byte stores)
@@ -66,7 +73,7 @@ __host__ __device__ constexpr int block_rows(int oct) {
   return oct == 0 ? 128 : oct == 1 ? 129 : 127 + (256 >> (8 - oct));  // 128, 129, 131, 135, 143, 159, 191
 }
 __host__ __device__ constexpr int block_rt(int oct) { return block_rows(oct) | 1; }
-__host__ __device__ constexpr int blocks_per_tile(int oct) { return oct == 0 ? 4 : oct == 1 ? 2 : 1; }
+__host__ __device__ constexpr int blocks_per_tile(int oct) { return oct == 0 ? 8 : oct == 1 ? 4 : oct == 2 ? 2 : 1; }
 }  // namespace cqt_tc
 
 #ifdef AST_TRACE
@@ -125,6 +132,7 @@ __device__ __forceinline__ void decode_tile(const CqtTcParams& p, int tile, int&
   t0 = (rem - b * p.tiles_per_clip_oct) * cqt_tc::kM;
 }
 
+// tid: thread index within its producer group (0..95)
 __device__ __forceinline__ BlockPlan plan_block(const CqtTcParams& p, int b, int oct, int t0, int j, int tid) {
   using namespace cqt_tc;
   BlockPlan s;
@@ -134,27 +142,27 @@ __device__ __forceinline__ BlockPlan plan_block(const CqtTcParams& p, int b, int
   s.len = (int)((len0 + (1LL << oct) - 1) >> oct);
   s.x = oct == 0 ? p.wave + (long long)b * p.wave_stride : p.ws + (long long)b * p.ws_clip_stride + p.oct_off[oct];
   s.vec_ok = oct == 0 ? p.vec_ok : true;
-  const int first = t0 * hop - kCqtNfft / 2 + 64 * j;  // first sample of the block (j > 0 only for octaves 0, 1)
+  const int first = t0 * hop - kCqtNfft / 2 + 32 * j;  // first sample of the block (j > 0 only for octaves 0..2)
   int n_chunks, last;
-  if (m >= 16) {
-    // 16 chunk columns: chunk u = tid + 224 i -> row R = (tid >> 4) + 14 i, column e = tid & 15
-    s.s0 = first + (tid >> 4) * hop + 4 * (tid & 15);
-    s.src_step = (kProducers / 16) * hop;
-    s.slot0 = (tid & 15) * rt + (tid >> 4);
-    s.slot_step = kProducers / 16;
-    n_chunks = 16 * rows;
-    last = first + (rows - 1) * hop + 64;
+  if (m >= kBlockCols) {
+    // eight chunk columns: chunk u = tg + 96 i -> row R = (tg >> 3) + 12 i, column e = tg & 7
+    s.s0 = first + (tid >> 3) * hop + 4 * (tid & 7);
+    s.src_step = (kGroupThreads / kBlockCols) * hop;
+    s.slot0 = (tid & 7) * rt + (tid >> 3);
+    s.slot_step = kGroupThreads / kBlockCols;
+    n_chunks = kBlockCols * rows;
+    last = first + (rows - 1) * hop + 32;
   } else {
-    // one contiguous run: chunk u = tid + 224 i -> row R = u / m, column e = u % m (m divides 224)
+    // one contiguous run: chunk u = tg + 96 i -> row R = u / m, column e = u % m (m divides 96)
     const int lg = 6 - oct;  // log2(m)
     s.s0 = first + 4 * tid;
-    s.src_step = 4 * kProducers;
+    s.src_step = 4 * kGroupThreads;
     s.slot0 = (tid & (m - 1)) * rt + (tid >> lg);
-    s.slot_step = kProducers >> lg;
+    s.slot_step = kGroupThreads >> lg;
     n_chunks = m * rows;
     last = first + 4 * n_chunks;
   }
-  s.n = tid < n_chunks ? (n_chunks - tid + kProducers - 1) / kProducers : 0;
+  s.n = tid < n_chunks ? (n_chunks - tid + kGroupThreads - 1) / kGroupThreads : 0;
   s.interior = first >= 0 && last <= s.len && s.vec_ok;
   s.coherent = oct > 0;
   s.dep = nullptr;
@@ -181,7 +189,7 @@ __device__ __forceinline__ void issue_block(uint32_t a_hi_addr, uint32_t b_addr,
   constexpr int m = (kHop >> OCT) >> 2;
   constexpr int rt = block_rt(OCT);
   constexpr uint32_t lbo = m == 1 ? 16u : (uint32_t)rt * 16u;
-  constexpr int n_steps = kKSteps / blocks_per_tile(OCT);  // 8, 16 or 32 K-steps per block
+  constexpr int n_steps = kKSteps / blocks_per_tile(OCT);  // 4, 8, 16 or 32 K-steps per block
   const uint64_t da_hi0 = umma::smem_desc(a_hi_addr, lbo, 128);
   const uint64_t da_lo0 = umma::smem_desc(a_hi_addr + kAFloats * 4, lbo, 128);
   const uint64_t db0 = umma::smem_desc(b_addr, 2 * kN * 16, 128);
@@ -191,21 +199,18 @@ __device__ __forceinline__ void issue_block(uint32_t a_hi_addr, uint32_t b_addr,
   for (int term = 0; term < 2; ++term) {
 #pragma unroll
     for (int i = 0; i < n_steps; ++i) {
-      int ks_c;        // K-step for j == 0 (compile time); the block index adds 8 j (octaves 0, 1)
+      int ks_c;        // K-step for j == 0 (compile time); the block index adds 4 j (octaves 0..2)
       int a_units;     // A start-address offset in 16-byte units
-      if (OCT == 0) {
-        ks_c = i;                                   // block j holds window chunks 16 j .. 16 j + 15
-        a_units = 2 * i * rt;
-      } else if (OCT == 1) {
-        const int d = i >> 3, k = i & 7;            // block j holds chunks 32 d + 16 j + e, e < 16, at row r + d
-        ks_c = 16 * d + k;
+      if (OCT <= 2) {
+        const int d = i >> 2, k = i & 3;            // block j holds chunks m d + 8 j + e, e < 8, at row r + d
+        ks_c = (m / 2) * d + k;
         a_units = 2 * k * rt + d;
       } else {
         const int c = 2 * i;
         ks_c = i;
         a_units = m == 1 ? c : (c / m) + (c % m) * rt;
       }
-      const uint64_t b_off = (uint64_t)((ks_c + (OCT <= 1 ? 8 * j : 0)) * (kBStepFloats / 4));
+      const uint64_t b_off = (uint64_t)((ks_c + (OCT <= 2 ? 4 * j : 0)) * (kBStepFloats / 4));
       const uint32_t acc = acc_set + (uint32_t)((ks_c & (kMainAcc - 1)) * 2 * kN);
       if (term == 0)  // hi * [hi | lo] -> columns 0..63 of the accumulator; the tile's first two K-steps overwrite
         umma::mma_tf32(acc, da_hi0 + (uint64_t)a_units, db0 + b_off, idesc64, (i >= kMainAcc || j > 0) ? 1u : 0u);
@@ -218,15 +223,17 @@ __device__ __forceinline__ void issue_block(uint32_t a_hi_addr, uint32_t b_addr,
 __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTcParams p) {
   using namespace cqt_tc;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* a_stage = reinterpret_cast<float*>(smem_raw);            // [2 stages][hi | lo]
-  float* b_img = a_stage + 2 * kStageFloats;                      // 64 KB
+  float* a_stage = reinterpret_cast<float*>(smem_raw);            // [4 stages][hi | lo]
+  float* b_img = a_stage + kStages * kStageFloats;                // 64 KB
   float* epi_buf = b_img + kBFloats;                              // [8 warps][32][25] epilogue transpose
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + kEpiFloats);
-  uint64_t* full = bars;            // [2] producers -> MMA   (7 arrivals: one per producer warp)
-  uint64_t* empty = bars + 2;       // [2] MMA -> producers   (tcgen05.commit)
-  uint64_t* acc_full = bars + 4;    // [2] MMA -> epilogue    (tcgen05.commit)
-  uint64_t* acc_empty = bars + 6;   // [2] epilogue -> MMA    (4 arrivals: one per epilogue warp)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  // stage s = block number % 4 always belongs to producer group s % 2, so every barrier is completed and waited in
+  // strict phase order by one party on each side
+  uint64_t* full = bars;            // [4] producers -> MMA   (3 arrivals: the warps of one producer group)
+  uint64_t* empty = bars + 4;       // [4] MMA -> producers   (tcgen05.commit)
+  uint64_t* acc_full = bars + 8;    // [2] MMA -> epilogue    (tcgen05.commit)
+  uint64_t* acc_empty = bars + 10;  // [2] epilogue -> MMA    (4 arrivals: one per epilogue warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   pdl_launch_dependents();
@@ -235,9 +242,11 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
     reinterpret_cast<float4*>(b_img)[i] = __ldg(reinterpret_cast<const float4*>(p.bmat) + i);
   if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, kTmemCols);
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      umma::mbar_init(full + i, kProducers / 32);
+    for (int i = 0; i < kStages; ++i) {
+      umma::mbar_init(full + i, kGroupThreads / 32);
       umma::mbar_init(empty + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       umma::mbar_init(acc_full + i, 1);
       umma::mbar_init(acc_empty + i, 4);
     }
@@ -253,7 +262,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
   if (!p.flags) pdl_wait();
   const int total = p.tiles_per_clip_oct * kOctaves * p.batch;  // gridDim.x <= total
 
-  if (warp < kProducers / 32) {
+  if (warp < kProducerWarps) {
     // ================================================================= producers
     // The loads of block k + 1 are issued right AFTER block k has been published: fence.proxy.async waits for every
     // outstanding load of the thread (measured: prefetching before the fence made the kernel 40 % slower), so the
@@ -315,16 +324,44 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
           if (i < sp.n) v[i] = umma::load4_zero_ext_cg(sp.x, sp.s0 + i * sp.src_step, sp.len);
       }
     };
-    int item = 0;
+    // group g takes blocks g, g + 2, g + 4, ... of this CTA's block sequence
+    const int grp = warp / 3, tg = tid - grp * kGroupThreads;
     int tile = blockIdx.x, j = 0;
     int b, oct, t0;
-    decode_tile(p, tile, b, oct, t0);
-    BlockPlan sp = plan_block(p, b, oct, t0, 0, tid);
-    issue_loads(sp);
-    while (tile < total) {
-      const int s = item & 1;
+    if (tile < total) decode_tile(p, tile, b, oct, t0);
+    auto advance = [&]() {  // next block: the same tile's next chunk columns, or the next tile's first block
+      if (++j == (oct == 0 ? 8 : oct == 1 ? 4 : oct == 2 ? 2 : 1)) {
+        tile += gridDim.x;
+        j = 0;
+        if (tile < total) decode_tile(p, tile, b, oct, t0);
+        // one thread asks L2 for the signal span of the tile after that one, so its loads find it there
+        if (tid == 0 && tile + (int)gridDim.x < total && !(p.debug & 8)) {
+          int b2, oct2, t2;
+          decode_tile(p, tile + gridDim.x, b2, oct2, t2);
+          const long long len2 = ((p.lengths ? p.lengths[b2] : p.max_samples) + (1LL << oct2) - 1) >> oct2;
+          const float* x2 = oct2 == 0 ? p.wave + (long long)b2 * p.wave_stride
+                                      : p.ws + (long long)b2 * p.ws_clip_stride + p.oct_off[oct2];
+          const int hop2 = kHop >> oct2;
+          long long lo = (long long)t2 * hop2 - kCqtNfft / 2, hi = lo + (long long)(kM - 1) * hop2 + kCqtNfft;
+          if (lo < 0) lo = 0;
+          if (hi > len2) hi = len2;
+          const uintptr_t a0 = (reinterpret_cast<uintptr_t>(x2 + lo) + 15) & ~(uintptr_t)15;
+          const uintptr_t a1 = reinterpret_cast<uintptr_t>(x2 + hi) & ~(uintptr_t)15;
+          if (a1 > a0) umma::prefetch_l2_bulk(reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0));
+        }
+      }
+    };
+    if (grp == 1 && tile < total) advance();   // group 1 starts at block 1
+    BlockPlan sp;
+    if (tile < total) {
+      sp = plan_block(p, b, oct, t0, j, tg);
+      issue_loads(sp);
+    }
+    for (int item = grp; tile < total; item += 2) {
+      const int s = item & (kStages - 1);
       if (warp == 0) AST_STAMP(0, item, 0);
-      umma::mbar_wait(empty + s, ((item >> 1) & 1) ^ 1);  // the MMAs that read this stage two blocks ago are done
+      // the MMAs that read this stage four blocks ago are done
+      umma::mbar_wait(empty + s, ((item >> 2) & 1) ^ 1);
       if (warp == 0) AST_STAMP(0, item, 2);
       float4* a_hi = reinterpret_cast<float4*>(a_stage + s * kStageFloats);
       float4* a_lo = a_hi + kAFloats / 4;
@@ -341,34 +378,14 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(full + s);
       if (warp == 0) AST_STAMP(0, item, 4);
-      // next block: the same tile's next chunk columns, or the next tile's first block
-      if (++j == (oct == 0 ? 4 : oct == 1 ? 2 : 1)) {
-        tile += gridDim.x;
-        j = 0;
-        if (tile < total) decode_tile(p, tile, b, oct, t0);
-        // one thread asks L2 for the signal span of the tile after that one, so its loads find it there
-        if (tid == 0 && tile + (int)gridDim.x < total && !(p.debug & 8)) {
-          int b2, oct2, t2;
-          decode_tile(p, tile + gridDim.x, b2, oct2, t2);
-          const long long len2 = ((p.lengths ? p.lengths[b2] : p.max_samples) + (1LL << oct2) - 1) >> oct2;
-          const float* x2 = oct2 == 0 ? p.wave + (long long)b2 * p.wave_stride
-                                      : p.ws + (long long)b2 * p.ws_clip_stride + p.oct_off[oct2];
-          const int hop2 = kHop >> oct2;
-          long long lo = (long long)t2 * hop2 - kCqtNfft / 2, hi = lo + (long long)(kM - 1) * hop2 + kCqtNfft;
-          if (lo < 0) lo = 0;
-          if (hi > len2) hi = len2;
-          // align to 16 bytes inside the range
-          const uintptr_t a0 = (reinterpret_cast<uintptr_t>(x2 + lo) + 15) & ~(uintptr_t)15;
-          const uintptr_t a1 = reinterpret_cast<uintptr_t>(x2 + hi) & ~(uintptr_t)15;
-          if (a1 > a0) umma::prefetch_l2_bulk(reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0));
-        }
-      }
+      // this group's next block is two blocks further
+      advance();
+      if (tile < total) advance();
       if (tile < total) {
-        sp = plan_block(p, b, oct, t0, j, tid);
+        sp = plan_block(p, b, oct, t0, j, tg);
         issue_loads(sp);
       }
       if (warp == 0) AST_STAMP(0, item, 1);
-      ++item;
     }
   } else if (warp == kMmaWarp) {
     // ================================================================= MMA issue
@@ -381,11 +398,11 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
       decode_tile(p, tile, b, oct, t0);
       umma::mbar_wait(acc_empty + q, ((n_tile >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator set
       umma::fence_after_thread_sync();
-      const int n_blocks = oct == 0 ? 4 : oct == 1 ? 2 : 1;
+      const int n_blocks = oct == 0 ? 8 : oct == 1 ? 4 : oct == 2 ? 2 : 1;
       for (int j = 0; j < n_blocks; ++j, ++item) {
-        const int s = item & 1;
+        const int s = item & (kStages - 1);
         AST_STAMP(1, item, 0);
-        umma::mbar_wait(full + s, (item >> 1) & 1);
+        umma::mbar_wait(full + s, (item >> 2) & 1);
         umma::fence_after_thread_sync();
         AST_STAMP(1, item, 1);
         if (umma::elect_one_sync()) {
@@ -407,7 +424,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
         AST_STAMP(1, item, 2);
       }
     }
-  } else {
+  } else if (warp >= kEpilogueWarp0) {
     // ================================================================= epilogue (warps 8-15)
     // TMEM holds one frame per lane; written that way every store instruction would touch 32 output rows
     // (32 L1 wavefronts for 128 B).  The 32 x 24 block is therefore transposed through shared memory and
