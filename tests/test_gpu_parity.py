@@ -442,3 +442,32 @@ def test_features_host_pipeline_equals_device_call(fe, piano_stats):
         assert got is host_out and torch.equal(host_out, ref.cpu()), chunk
     with pytest.raises(ValueError):
         fe.features_host(wave, torch.empty(1, 2, 3))
+
+
+@pytest.mark.parametrize("env", [{"AST_DECIMATOR": "fma"}, {"AST_CQT": "fma"}, {"AST_DECIMATOR": "fma", "AST_CQT": "fma"},
+                                 {"AST_OVERLAP": "0"}])
+def test_diagnostic_kernel_variants_agree(fe, tmp_path, env):
+    """The FMA-pipe twins of the two tensor-core kernels (AST_DECIMATOR=fma, AST_CQT=fma) and the serial launch order
+    (AST_OVERLAP=0) are diagnostics of the same library, selected when a plan is created: run them in a fresh process
+    and compare with the default path (and so, transitively, with the oracle)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    wave = np.stack([synth.clip("piano", 300, 50000), synth.clip("violin", 301, 50000)])
+    np.save(tmp_path / "wave.npy", wave)
+    code = (
+        "import importlib, sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "fe = importlib.import_module('audio_style_transfer_b200.frontend').FrontEnd('cuda:0')\n"
+        f"x = torch.from_numpy(np.load({str(tmp_path / 'wave.npy')!r})).cuda()\n"
+        "f, n = fe.features(x, layout='flat')\n"
+        f"np.save({str(tmp_path / 'out.npy')!r}, f.cpu().numpy())\n")
+    subprocess.run([sys.executable, "-c", code], check=True, env={**os.environ, **env}, timeout=300)
+    got = np.load(tmp_path / "out.npy")
+    ref, _ = fe.features(cuda(wave), layout="flat")
+    ref = ref.cpu().numpy()
+    assert got.shape == ref.shape
+    assert np.array_equal(got[..., :513], ref[..., :513])                       # the STFT does not depend on the switches
+    assert np.abs(got[..., 513:] - ref[..., 513:]).max() <= 1e-5 * np.abs(ref[..., 513:]).max()
