@@ -36,7 +36,7 @@ void profile_mark(const char* name, cudaStream_t st, bool begin) {
   }
 }
 
-static int g_overlap_streams = 1;  // AST_OVERLAP=0 serialises the two branches on the caller's stream
+static int g_overlap_streams = 1;  // AST_OVERLAP=0: plain launch order STFT, decimator, CQT (no programmatic overlap of the STFT)
 void set_overlap_streams(int on) { g_overlap_streams = on; }
 
 static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }

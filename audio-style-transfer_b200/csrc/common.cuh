@@ -162,7 +162,6 @@ struct ast_plan {
   float* d_hann_sq;     // Hann^2 (iSTFT envelope)
   float* d_cqt_kernel;  // [256][24] base time-domain CQT kernel (12 re then 12 im columns)
   float* d_cqt_scale;   // [7][12] per octave / bin scale sqrt(2^i) / sqrt(length_k)
-  cudaStream_t side_stream;  // non-blocking stream for the tensor-pipe branch of ast_features_forward
   float* d_cqt_tc_images;  // CQT kernel as TF32 hi / lo B-operand images per pass (cqt_tc.cu)
   float* d_dec_strip_hi;  // decimator Toeplitz strip, TF32 hi part (smem image, decimate.cu)
   float* d_dec_strip_lo;  // ... and the TF32 residual

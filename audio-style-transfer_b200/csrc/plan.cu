@@ -341,8 +341,6 @@ int ast_plan_create(const ast_config* cfg, ast_plan** out) {
   if (rc == AST_OK) rc = istft_init();
   if (rc == AST_OK) rc = decimate_init();
   if (rc == AST_OK) rc = cqt_tc_init();
-  if (rc == AST_OK && cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking) != cudaSuccess)
-    rc = fail(AST_ERR_CUDA, "cannot create the side stream");
   if (const char* env = std::getenv("AST_OVERLAP")) set_overlap_streams(std::strcmp(env, "0") != 0);
   if (const char* env = std::getenv("AST_CQT"))  // diagnostic A/B switch: "fma" selects the FMA-pipe projection
     set_tc_cqt(std::strcmp(env, "fma") != 0);
@@ -365,7 +363,6 @@ int ast_plan_destroy(ast_plan* p) {
   cudaFree(p->d_hann_sq);
   cudaFree(p->d_cqt_kernel);
   cudaFree(p->d_cqt_scale);
-  if (p->side_stream) cudaStreamDestroy(p->side_stream);
   cudaFree(p->d_cqt_tc_images);
   cudaFree(p->d_dec_strip_hi);
   cudaFree(p->d_dec_strip_lo);
