@@ -133,7 +133,8 @@ __device__ __forceinline__ void decode_tile(const CqtTcParams& p, int tile, int&
 }
 
 // tid: thread index within its producer group (0..95)
-__device__ __forceinline__ BlockPlan plan_block(const CqtTcParams& p, int b, int oct, int t0, int j, int tid) {
+__device__ __forceinline__ BlockPlan plan_block(const CqtTcParams& p, int b, int oct, int t0, int j, int tid,
+                                                unsigned stages_complete) {
   using namespace cqt_tc;
   BlockPlan s;
   const long long len0 = p.lengths ? p.lengths[b] : p.max_samples;
@@ -167,7 +168,7 @@ __device__ __forceinline__ BlockPlan plan_block(const CqtTcParams& p, int b, int
   s.coherent = oct > 0;
   s.dep = nullptr;
   s.dep_n = 0;
-  if (oct > 0 && p.flags) {
+  if (oct > 0 && p.flags && !((stages_complete >> (oct - 1)) & 1)) {  // (a finished stage needs no bookkeeping)
     // decimator stage oct - 1 produced samples [lo, hi) of this octave in tiles lo / 7424 ... (hi - 1) / 7424
     const int lo = first > 0 ? first : 0, hi = last < s.len ? last : s.len;
     if (hi > lo) {
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
     if (grp == 1 && tile < total) advance();   // group 1 starts at block 1
     BlockPlan sp;
     if (tile < total) {
-      sp = plan_block(p, b, oct, t0, j, tg);
+      sp = plan_block(p, b, oct, t0, j, tg, stages_complete);
       issue_loads(sp);
     }
     for (int item = grp; tile < total; item += 2) {
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
       advance();
       if (tile < total) advance();
       if (tile < total) {
-        sp = plan_block(p, b, oct, t0, j, tg);
+        sp = plan_block(p, b, oct, t0, j, tg, stages_complete);
         issue_loads(sp);
       }
       if (warp == 0) AST_STAMP(0, item, 1);
