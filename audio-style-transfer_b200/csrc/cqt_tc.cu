@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
           return;
         }
       }
+      unsigned long long t_first = 0;
       for (uint32_t spin = 0;; ++spin) {
         int ok = 1;
         if (lane == 0) {
@@ -299,7 +300,11 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
         }
         if (__shfl_sync(0xffffffffu, ok, 0)) return;
         __nanosleep(200);
-        if (spin > (1u << 24)) __trap();
+        if ((spin & 1023) == 1023) {
+          const unsigned long long now = umma::global_ns();
+          if (t_first == 0) t_first = now;
+          if (now - t_first > umma::kPollTimeoutNs) __trap();
+        }
       }
     };
     auto issue_loads = [&](const BlockPlan& sp) {

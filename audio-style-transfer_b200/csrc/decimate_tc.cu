@@ -204,9 +204,14 @@ __device__ __forceinline__ bool dtc_deps_ready(const DecimateTcParams& p, const 
 
 // Bounded wait: a broken dependency chain traps (kernel error) instead of hanging the GPU.
 __device__ __forceinline__ void dtc_deps_wait(const DecimateTcParams& p, const DtcTile& t, int lane, unsigned& stages_complete) {
+  unsigned long long t0 = 0;
   for (uint32_t spin = 0; !dtc_deps_ready(p, t, lane, stages_complete); ++spin) {
     __nanosleep(200);
-    if (spin > (1u << 24)) __trap();
+    if ((spin & 1023) == 1023) {
+      const unsigned long long now = umma::global_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > umma::kPollTimeoutNs) __trap();
+    }
   }
 }
 
@@ -489,9 +494,14 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
       if (lane == 0) {
         if (t.live) {
           ++n;
+          unsigned long long t0 = 0;
           for (uint32_t spin = 0; *reinterpret_cast<volatile unsigned int*>(stored_count) < 4u * (unsigned)n; ++spin) {
             __nanosleep(100);
-            if (spin > (1u << 26)) __trap();
+            if ((spin & 1023) == 1023) {
+              const unsigned long long now = umma::global_ns();
+              if (t0 == 0) t0 = now;
+              if (now - t0 > umma::kPollTimeoutNs) __trap();
+            }
           }
           __threadfence();   // every stage: the CQT projection that follows polls the same counters
           atomicAdd(dtc_flag(p, t.stage, t.clip, t.k), 4);

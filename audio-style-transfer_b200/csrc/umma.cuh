@@ -49,6 +49,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// wall-clock nanoseconds (for the bounds of the cross-CTA polling loops: a count of polls would also trip under a
+// sanitizer or a debugger, where everything runs orders of magnitude slower)
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kPollTimeoutNs = 20ull * 1000 * 1000 * 1000;  // 20 s: nothing here legitimately waits that long
+
 // Bounded wait: a broken pipeline traps (kernel error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
