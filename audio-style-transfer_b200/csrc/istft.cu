@@ -16,6 +16,8 @@
 // overlap-add runs in registers: no atomics, no shared-memory frame store, deterministic order
 // (frames ascending, like torch's fold).  A run of R segments needs 4 halo frames.
 // Shared memory per CTA: 16.1 KB exchange buffers (twiddles come from global memory through L1): 12 CTAs / SM.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ast {
@@ -283,6 +285,10 @@ int launch_istft(const ast_plan* plan, const float* spec, int batch, int dim1, i
     const double per_cta = r + 4;                       // frames per run incl. halo
     const double cost = waves * per_cta;                // time ~ waves x work per CTA
     if (cost < best * 0.999) best = cost, best_r = r;
+  }
+  if (const char* env = getenv("AST_ISTFT_RUN")) {  // diagnostic override of the run length
+    const int r = atoi(env);
+    if (r >= 2 && r <= 4096) best_r = r & ~1;
   }
   p.run_segs = best_r;
   dim3 grid((unsigned)((segs + best_r - 1) / best_r), (unsigned)batch);
