@@ -2,7 +2,9 @@
 
 ``mse_spectrogram`` keeps the signature of ``evaluation_reconstruction.py:105-118`` /
 ``evaluation_style_transfer.py:111-119`` (NumPy arrays or tensors in, Python float out, ``inf`` on failure) and
-runs both STFTs and the reduction on the device; ``reconstruct_audio_from_sections`` keeps
+runs both STFTs and the reduction on the device; ``instrumentation_similarity`` keeps
+``evaluation_style_transfer.py:111-119`` (two 2048-point STFTs, per-bin energy profiles and their Pearson
+correlation in one pass on the device); ``reconstruct_audio_from_sections`` keeps
 ``evaluation_reconstruction.py:161-189`` (section 0 only, ``np.zeros(22050)`` on any exception).
 """
 from __future__ import annotations
@@ -47,6 +49,27 @@ def mse_spectrogram(original_audio, generated_audio, sr=22050):
     except Exception as e:  # the reference prints and returns inf
         print(f"Error in mse_spectrogram: {e}")
         return float("inf")
+
+
+def instrumentation_similarity_device(audio1, audio2) -> torch.Tensor:
+    """The correlation as a 0-d float64 tensor on the device (no host synchronisation)."""
+    dev = _cuda_device(audio1 if isinstance(audio1, torch.Tensor) else None)
+    fe = default_frontend(dev)
+    a, b = _device_signal(audio1, fe.device), _device_signal(audio2, fe.device)
+    nbytes = fe.lib.ast_instrumentation_similarity_workspace_bytes(fe._plan, a.numel(), b.numel())
+    ws = fe._workspace(nbytes)
+    out = torch.empty(1, dtype=torch.float64, device=fe.device)
+    with torch.cuda.device(fe.device):
+        _lib.check(fe.lib.ast_instrumentation_similarity(fe._plan, _ptr(a), a.numel(), _ptr(b), b.numel(), _ptr(ws), nbytes,
+                                                         _ptr(out), _stream_ptr(fe.device)))
+    return out[0]
+
+
+def instrumentation_similarity(audio1, audio2, sr=22050):
+    """``evaluation_style_transfer.instrumentation_similarity`` (``:111-119``): Pearson correlation of the per-bin
+    energy profiles of ``|librosa.stft(audio)|`` (n_fft 2048, hop 512); 0.0 where the reference's is NaN.  Like the
+    reference it does not catch exceptions (an empty signal raises)."""
+    return float(instrumentation_similarity_device(audio1, audio2).item())
 
 
 def reconstruct_audio_from_sections(sections_tensor):

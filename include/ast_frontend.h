@@ -229,6 +229,17 @@ size_t ast_mse_workspace_bytes(const ast_plan* plan, int64_t n_a, int64_t n_b);
 int ast_mse_spectrogram(const ast_plan* plan, const float* a, int64_t n_a, const float* b, int64_t n_b,
                         void* workspace, size_t workspace_bytes, double* result, void* stream);
 
+/*
+ * replaces instrumentation_similarity (evaluation_style_transfer.py:111-119): Pearson correlation between the
+ * per-bin sums over time of |librosa.stft(a)| and |librosa.stft(b)| (librosa defaults: n_fft = 2048, hop = 512,
+ * center=True with ZERO padding, periodic Hann -> 1025 bins); 0.0 where the reference's pearsonr returns NaN
+ * (a constant energy profile, e.g. silence).
+ *   a, b     mono signals on the device (n_a, n_b samples, both >= 1); result: 1 double on the device
+ */
+size_t ast_instrumentation_similarity_workspace_bytes(const ast_plan* plan, int64_t n_a, int64_t n_b);
+int ast_instrumentation_similarity(const ast_plan* plan, const float* a, int64_t n_a, const float* b, int64_t n_b,
+                                   void* workspace, size_t workspace_bytes, double* result, void* stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /*
  * Per-kernel device timing (no counterpart in the reference).  While enabled, every kernel launch

@@ -1,5 +1,6 @@
-"""mse_spectrogram (evaluation_reconstruction.py:105-118): oracle vs torch.stft with constant padding
-(CPU; librosa itself is not installable here), CUDA path vs the oracle (GPU)."""
+"""mse_spectrogram (evaluation_reconstruction.py:105-118) and instrumentation_similarity
+(evaluation_style_transfer.py:111-119), SURVEY.md 8f-4: oracle vs torch.stft with constant padding (CPU; librosa
+itself is not installable here), CUDA path vs the oracle (GPU)."""
 import importlib
 
 import numpy as np
@@ -66,3 +67,54 @@ def test_gpu_reconstruct_audio_from_sections_mirror():
     assert y.shape == ref.shape == (73216,) and np.abs(y - ref).max() <= 2e-5
     bad = ev.reconstruct_audio_from_sections(torch.zeros(1, 4, 2, 287, 100))   # wrong bin count -> the reference's fallback
     assert bad.shape == (22050,) and not bad.any()
+
+
+@pytest.mark.parametrize("n", [700, 22050, 50001])
+def test_oracle_default_stft_magnitude_equals_torch_constant_pad(n):
+    # librosa.stft defaults (instrumentation_similarity): n_fft 2048, hop 512
+    a, _ = signals(4, n)
+    ref = torch.stft(torch.from_numpy(a), 2048, 512, window=torch.hann_window(2048), center=True, pad_mode="constant",
+                     return_complex=True).abs().numpy()
+    got = om.librosa_stft_mag(a, n_fft=2048, hop_length=512)
+    assert got.shape == ref.shape == (1025, 1 + n // 512)
+    assert np.abs(got - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1.0)
+
+
+def test_oracle_instrumentation_similarity_properties():
+    a, b = signals(5, 40000)
+    assert abs(om.instrumentation_similarity(a, a) - 1.0) <= 1e-6
+    r = om.instrumentation_similarity(a, b)
+    assert -1.0 <= r <= 1.0 and abs(om.instrumentation_similarity(b, a) - r) <= 1e-6
+    # a gain does not change the correlation; silence has a constant profile -> NaN -> 0.0 (:119)
+    assert abs(om.instrumentation_similarity(a, 0.25 * b) - r) <= 1e-5
+    assert om.instrumentation_similarity(a, np.zeros(40000, np.float32)) == 0.0
+    # a sine against noise: the noise profile is flat, the sine's is a single peak
+    t = np.arange(40000) / 22050.0
+    tone = (0.3 * np.sin(2 * np.pi * 440.0 * t)).astype(np.float32)
+    noise = np.random.default_rng(0).standard_normal(40000).astype(np.float32)
+    assert abs(om.instrumentation_similarity(tone, noise)) < 0.2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("na,nb", [(300, 900), (700, 700), (22050, 22050), (219904, 220500), (50001, 40000), (661500, 220500)])
+def test_gpu_instrumentation_similarity_matches_oracle(na, nb):
+    ev = importlib.import_module("audio_style_transfer_b200.evaluation")
+    a, _ = signals(6, max(na, 64))
+    _, b = signals(7, max(nb, 64))
+    a, b = a[:na], b[:nb]
+    ref = om.instrumentation_similarity(a, b)
+    got = ev.instrumentation_similarity(a, b)
+    assert isinstance(got, float) and abs(got - ref) <= 2e-5
+    assert abs(ev.instrumentation_similarity(a, a) - 1.0) <= 1e-6
+    got2 = ev.instrumentation_similarity(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+    assert got2 == got                     # deterministic; device tensors accepted
+
+
+@pytest.mark.gpu
+def test_gpu_instrumentation_similarity_silence_and_errors():
+    ev = importlib.import_module("audio_style_transfer_b200.evaluation")
+    a, _ = signals(8, 30000)
+    assert ev.instrumentation_similarity(a, np.zeros(30000, np.float32)) == 0.0
+    assert ev.instrumentation_similarity(np.zeros(100, np.float32), np.zeros(100, np.float32)) == 0.0
+    with pytest.raises(RuntimeError):
+        ev.instrumentation_similarity(a, np.zeros(0, np.float32))
