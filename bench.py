@@ -231,6 +231,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    hostmem = importlib.import_module("audio_style_transfer_b200.hostmem")
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     frontend = importlib.import_module("audio_style_transfer_b200.frontend")
@@ -348,8 +349,10 @@ def main():
     # ---- end to end through the public API with HOST buffers (pinned): H2D + kernels + D2H per step
     e2e = None
     if not args.no_e2e:
-        host_in = torch.from_numpy(wave_np).pin_memory()
-        host_out = torch.empty(out.shape, dtype=torch.float32).pin_memory()
+        # pinned staging buffers on the GPU's own NUMA node (pages are placed when they are allocated)
+        with hostmem.device_local_affinity(device) as numa:
+            host_in = torch.from_numpy(wave_np).pin_memory()
+            host_out = torch.empty(out.shape, dtype=torch.float32).pin_memory()
 
         def e2e_step():
             fe.features_host(host_in, host_out, mean=mean_d, std=std_d)
@@ -367,7 +370,7 @@ def main():
             dt = float(t[0])
         e2e = {"value": world * CLIPS_PER_GPU * CLIP_SECONDS * e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(host_in.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4),
-               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps, "numa": numa,
                "how": "FrontEnd.features_host: pinned host waveforms -> H2D -> ast_features_forward -> D2H of the full 351 MB "
                       "feature tensor into pinned host memory, 16-clip chunks pipelined over 3 streams, synchronize every step"}
 
