@@ -41,9 +41,21 @@ constexpr int kBuf1Stride = 65;   // float2 per k1 row
 constexpr int kBuf1Size = 16 * kBuf1Stride;
 constexpr int kBuf2Size = 1024;
 
+// On the device the complex helpers are the packed FP32x2 instructions of sm_100 (FADD2 / FMUL2 / FFMA2: one issue
+// slot per complex add, two per complex multiply; the swaps and sign flips of mul_neg_i and of the multiply fold into
+// the instructions' operand modifiers).  Same roundings as the scalar forms: (a.x b.x - round(a.y b.y)) fused once.
+#if defined(__CUDA_ARCH__)
+AST_HD float2 cmul(float2 a, float2 b) {
+  const float2 q = __fmul2_rn(make_float2(a.y, a.y), make_float2(b.y, b.x));
+  return __ffma2_rn(make_float2(a.x, a.x), b, make_float2(-q.x, q.y));
+}
+AST_HD float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+AST_HD float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+#else
 AST_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 AST_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 AST_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 // multiply by -i  (forward W_4^1)
 AST_HD float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }
 
