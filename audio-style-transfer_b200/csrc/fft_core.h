@@ -160,6 +160,14 @@ AST_HD void separate_pair(int k, float2 zk, float2 zp, Emit& emit) {
     emit(k, zk.x + zp.x, zk.y - zp.y, zk.y + zp.y, zp.x - zk.x);
 }
 
+// bin emitted by the i-th emit() call of fft1024_stage3_real_pair in thread j (i < 8, thread 0: i < 9); lets a caller
+// fetch per-bin constants ahead of the transform's last stage
+AST_HD int fft1024_stage3_bin(int j, int i) {
+  const int a[9] = {j, 256 + j, 512 - j, 256 - j, 128 - j, 384 - j, 384 + j, 128 + j, 0};
+  const int z[9] = {0, 256, 512, 128, 384, 64, 320, 448, 192};
+  return j != 0 ? a[i] : z[i];
+}
+
 // stage 3 of the forward transform of two real frames: emits all 513 bins of both frames.
 // emit(k, a_re, a_im, b_re, b_im).  Thread j emits 8 bins (thread 0: 9).
 template <bool kHalve, class Emit>

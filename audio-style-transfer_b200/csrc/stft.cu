@@ -5,18 +5,26 @@
 // for the STFT columns of the feature tensor.
 //
 // One group of 64 threads owns one frame pair (frames 2p and 2p+1 share one complex FFT, and
-// share 3/4 of their samples: 20 strided loads feed both).  A 256-thread CTA runs four groups in
+// share 3/4 of their samples: 20 strided loads feed both).  A 128-thread CTA runs two groups in
 // lock step over `iters` consecutive groups of pairs of ONE clip (grid = pair tiles x clips), so all
 // per-clip bookkeeping is CTA-uniform.  Interior frames take a check-free load path; rows whose
-// destinations are all live take a select-free store path.  Shared memory per CTA: 10 KB twiddle
-// tables + 4 x (8320 B + 8192 B) exchange buffers = 76 288 B.
+// destinations are all live take a select-free store path.  The (mean, rstd) pairs of the bins a thread
+// emits are fetched before the barrier that precedes stage 3, so their L2 round trip overlaps it.
+// Shared memory per CTA: 10 KB twiddle tables + 2 x (8320 B + 8192 B) exchange buffers = 43 264 B;
+// four CTAs (16 warps, 128 registers per thread, no spills) per SM.  The shape is the best of a sweep, ms per
+// 64 clips (groups per CTA x CTAs per SM): 4x3 at 80 registers without the early statistics fetch 0.149 (with it:
+// spills, 0.176), 4x2 0.157, 5x2 0.159, 3x3 0.156, 1x8 0.151, 2x5 at 96 registers 0.144, 2x4 at 128 registers 0.140
+// (0.143 without the early fetch; prefetching the next pair's samples on top spills again, 0.151).
 #include <cstdlib>
 
 #include "common.cuh"
 
 namespace ast {
 
-constexpr int kStftGroups = 4;
+#ifndef AST_STFT_GROUPS
+#define AST_STFT_GROUPS 2   // frame-pair groups (of 64 threads) per CTA
+#endif
+constexpr int kStftGroups = AST_STFT_GROUPS;
 constexpr int kStftThreads = kStftGroups * kFftThreads;
 constexpr size_t kStftSmem = sizeof(float2) * (kTw1Size + kTw2Size + kStftGroups * (kBuf1Size + kBuf2Size));
 
@@ -38,6 +46,17 @@ struct StftParams {
 
 // Destination of the two frames of a pair: up to two rows each (a frame inside the overlap of two
 // sections is stored twice).  kAllLive: every present row receives data (no zero padding involved).
+// compile-time switches kept for the shape sweep (scratch/run_variants.sh)
+#ifndef AST_STFT_PRELOAD
+#define AST_STFT_PRELOAD 1  // 1: per-bin statistics fetched ahead of the stage-3 barrier (36 live registers)
+#endif
+#ifndef AST_STFT_CTAS
+#define AST_STFT_CTAS 4     // resident CTAs per SM the register allocation is sized for
+#endif
+#ifndef AST_STFT_PREFETCH
+#define AST_STFT_PREFETCH 0 // 1: the next interior pair's 20 samples are loaded right after stage 1 (20 more live registers)
+#endif
+
 template <bool kAllLive>
 struct StftEmit {
   float* a0;
@@ -46,20 +65,37 @@ struct StftEmit {
   float* b1;            // channel-0 row bases (nullptr: absent)
   bool la0, la1, lb0, lb1;
   long long plane;      // floats from the channel-0 row to the channel-1 row
+#if AST_STFT_PRELOAD
+  // (mean, rstd) of the bins this thread emits, in emit order (fft1024_stage3_bin), fetched before the barrier that
+  // precedes stage 3 so that their L2 round trip overlaps it
+  const float2 (&m0)[9];
+  const float2 (&m1)[9];
+  bool has_stats;
+  int idx;              // emit() calls so far: compile-time after inlining, the arrays stay in registers
+#else
   const float2* st0;    // (mean, rstd) of channel 0, or nullptr
   const float2* st1;
+#endif
   // values arrive WITHOUT the factor 1/2 of the Hermitian separation; x = 0.5 s is exact, so
   // fmaf(s, 0.5, -mean) rounds once, exactly like the reference's (x - mean).
-  __device__ __forceinline__ void operator()(int k, float are, float aim, float bre, float bim) const {
+  __device__ __forceinline__ void operator()(int k, float are, float aim, float bre, float bim) {
+#if AST_STFT_PRELOAD
+    if (has_stats) {
+      const float2 s0 = m0[idx], s1 = m1[idx];
+#else
     if (st0) {
-      const float2 m0 = __ldg(st0 + k), m1 = __ldg(st1 + k);
-      are = fmaf(are, 0.5f, -m0.x) * m0.y;
-      bre = fmaf(bre, 0.5f, -m0.x) * m0.y;
-      aim = fmaf(aim, 0.5f, -m1.x) * m1.y;
-      bim = fmaf(bim, 0.5f, -m1.x) * m1.y;
+      const float2 s0 = __ldg(st0 + k), s1 = __ldg(st1 + k);
+#endif
+      are = fmaf(are, 0.5f, -s0.x) * s0.y;
+      bre = fmaf(bre, 0.5f, -s0.x) * s0.y;
+      aim = fmaf(aim, 0.5f, -s1.x) * s1.y;
+      bim = fmaf(bim, 0.5f, -s1.x) * s1.y;
     } else {
       are *= 0.5f, aim *= 0.5f, bre *= 0.5f, bim *= 0.5f;
     }
+#if AST_STFT_PRELOAD
+    ++idx;
+#endif
     if (kAllLive) {
       a0[k] = are;
       a0[plane + k] = aim;
@@ -111,7 +147,7 @@ __device__ __forceinline__ void frame_rows(const OutSpec& o, int b, int t, int f
   }
 }
 
-__global__ void __launch_bounds__(kStftThreads, 3) stft_kernel(const StftParams p) {
+__global__ void __launch_bounds__(kStftThreads, AST_STFT_CTAS) stft_kernel(const StftParams p) {
   extern __shared__ __align__(16) float2 smem[];
   float2* t1 = smem;
   float2* t2 = smem + kTw1Size;
@@ -140,6 +176,10 @@ __global__ void __launch_bounds__(kStftThreads, 3) stft_kernel(const StftParams 
   const bool no_store = p.debug & 1;
   __syncthreads();
 
+#if AST_STFT_PREFETCH
+  float xv[20];          // samples of the next interior pair, in flight across stages 2 and 3 of the current one
+  bool have_xv = false;
+#endif
   for (int it = 0; it < p.iters; ++it) {
     const int pair = (blockIdx.x * p.iters + it) * kStftGroups + group;
     const bool active = pair < p.pairs_per_clip;
@@ -151,10 +191,18 @@ __global__ void __launch_bounds__(kStftThreads, 3) stft_kernel(const StftParams 
       const bool interior = ta >= 2 && (ta + 1) * kHop + kNfft / 2 <= len;
       if (interior) {
         // frame B sample n is frame A sample n + 256: x[base + 64 j], j = 0..19, feeds both
+#if AST_STFT_PREFETCH
+        if (!have_xv) {
+          const float* __restrict__ xp = x + base;
+#pragma unroll
+          for (int j = 0; j < 20; ++j) xv[j] = __ldg(xp + 64 * j);
+        }
+#else
         const float* __restrict__ xp = x + base;
         float xv[20];
 #pragma unroll
         for (int j = 0; j < 20; ++j) xv[j] = __ldg(xp + 64 * j);
+#endif
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) v[n1] = make_float2(xv[n1] * win[n1], xv[n1 + 4] * win[n1]);
       } else {
@@ -169,8 +217,35 @@ __global__ void __launch_bounds__(kStftThreads, 3) stft_kernel(const StftParams 
       }
       fft1024_stage1(v, tid, t1, buf1);
     }
+#if AST_STFT_PREFETCH
+    {
+      const int tn = ta + 2 * kStftGroups;   // this group's pair of the next iteration
+      have_xv = it + 1 < p.iters && tn >= 2 && (tn + 1) * kHop + kNfft / 2 <= len;
+      if (have_xv) {
+        const float* __restrict__ xp = x + (tn * kHop - kNfft / 2 + tid);
+#pragma unroll
+        for (int j = 0; j < 20; ++j) xv[j] = __ldg(xp + 64 * j);
+      }
+    }
+#endif
     __syncthreads();
-    if (any_live) fft1024_stage2(tid, t2, buf1, buf2);
+#if AST_STFT_PRELOAD
+    float2 m0[9], m1[9];
+#endif
+    if (any_live) {
+      fft1024_stage2(tid, t2, buf1, buf2);
+#if AST_STFT_PRELOAD
+      if (st0) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          if (i < 8 || tid == 0) {
+            const int k = fft1024_stage3_bin(tid, i);
+            m0[i] = __ldg(st0 + k), m1[i] = __ldg(st1 + k);
+          }
+        }
+      }
+#endif
+    }
     __syncthreads();
     if (active) {
       float *a0, *a1, *b0 = nullptr, *b1 = nullptr;
@@ -180,14 +255,26 @@ __global__ void __launch_bounds__(kStftThreads, 3) stft_kernel(const StftParams 
       if (no_store) a0 = a1 = b0 = b1 = nullptr, la0 = false;  // diagnostic: all stores predicated off (not-all-live path)
       const bool all_live = la0 && (la1 || !a1) && (lb0 || !b0) && (lb1 || !b1);
       if (any_live && all_live) {
+#if AST_STFT_PRELOAD
+        StftEmit<true> emit{a0, a1, b0, b1, true, true, true, true, plane, m0, m1, st0 != nullptr, 0};
+#else
         StftEmit<true> emit{a0, a1, b0, b1, true, true, true, true, plane, st0, st1};
+#endif
         fft1024_stage3_real_pair<false>(tid, buf2, emit);
       } else if (any_live) {
+#if AST_STFT_PRELOAD
+        StftEmit<false> emit{a0, a1, b0, b1, la0, la1, lb0, lb1, plane, m0, m1, st0 != nullptr, 0};
+#else
         StftEmit<false> emit{a0, a1, b0, b1, la0, la1, lb0, lb1, plane, st0, st1};
+#endif
         fft1024_stage3_real_pair<false>(tid, buf2, emit);
       } else {
         // both frames lie past the clip: their rows exist in the output and must be zeros
+#if AST_STFT_PRELOAD
+        StftEmit<false> emit{a0, a1, b0, b1, false, false, false, false, plane, m0, m1, false, 0};
+#else
         StftEmit<false> emit{a0, a1, b0, b1, false, false, false, false, plane, nullptr, nullptr};
+#endif
         for (int k = tid; k < kFStft; k += kFftThreads) emit(k, 0.f, 0.f, 0.f, 0.f);
       }
     }
