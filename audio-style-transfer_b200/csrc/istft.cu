@@ -15,7 +15,7 @@
 // contribution to output position (segment g, offset q) is therefore produced by the SAME thread, so the
 // overlap-add runs in registers: no atomics, no shared-memory frame store, deterministic order
 // (frames ascending, like torch's fold).  A run of R segments needs 4 halo frames.
-// Shared memory per CTA: 16.1 KB exchange buffers (twiddles come from global memory through L1): 12 CTAs / SM.
+// Shared memory per CTA: 16.1 KB exchange buffers (twiddles come from global memory through L1); 8 CTAs / SM.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -176,10 +176,16 @@ __device__ __forceinline__ void emit_segments(const IstftParams& p, const OlaEmi
   }
 }
 
-__global__ void __launch_bounds__(kIstftThreads, 10) istft_kernel(const IstftParams p) {
+// resident CTAs per SM the register allocation is sized for: 8 -> 128 registers, no spills, 0.1355 ms per 64 clips;
+// 10 -> 102 registers, 148 B of spills, 0.1415; 9 -> 0.1405; 12 -> 80 registers, 0.215.  (An L1 prefetch of the next
+// pair's rows after stage 1 made it slower at every occupancy: 0.146 - 0.152.)
+#ifndef AST_ISTFT_CTAS
+#define AST_ISTFT_CTAS 8
+#endif
+__global__ void __launch_bounds__(kIstftThreads, AST_ISTFT_CTAS) istft_kernel(const IstftParams p) {
   extern __shared__ __align__(16) float2 smem[];
   const float2* __restrict__ t1 = p.t1;  // 10 KB of twiddles stay L1-resident; shared memory is kept for the
-  const float2* __restrict__ t2 = p.t2;  // exchange buffers so that 12 CTAs fit on an SM
+  const float2* __restrict__ t2 = p.t2;  // exchange buffers
   float2* buf1 = smem;
   float2* buf2 = buf1 + kBuf1Size;
   const int tid = threadIdx.x;

@@ -54,7 +54,8 @@ struct StftParams {
 #define AST_STFT_CTAS 4     // resident CTAs per SM the register allocation is sized for
 #endif
 #ifndef AST_STFT_PREFETCH
-#define AST_STFT_PREFETCH 0 // 1: the next interior pair's 20 samples are loaded right after stage 1 (20 more live registers)
+#define AST_STFT_PREFETCH 2 // 1: the next interior pair's 20 samples are loaded right after stage 1 (20 more live registers, spills)
+                            // 2: the 512 samples of the next pair that this iteration has not touched are prefetched into the L1
 #endif
 
 template <bool kAllLive>
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(kStftThreads, AST_STFT_CTAS) stft_kernel(const
   const bool no_store = p.debug & 1;
   __syncthreads();
 
-#if AST_STFT_PREFETCH
+#if AST_STFT_PREFETCH == 1
   float xv[20];          // samples of the next interior pair, in flight across stages 2 and 3 of the current one
   bool have_xv = false;
 #endif
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(kStftThreads, AST_STFT_CTAS) stft_kernel(const
       const bool interior = ta >= 2 && (ta + 1) * kHop + kNfft / 2 <= len;
       if (interior) {
         // frame B sample n is frame A sample n + 256: x[base + 64 j], j = 0..19, feeds both
-#if AST_STFT_PREFETCH
+#if AST_STFT_PREFETCH == 1
         if (!have_xv) {
           const float* __restrict__ xp = x + base;
 #pragma unroll
@@ -217,7 +218,17 @@ __global__ void __launch_bounds__(kStftThreads, AST_STFT_CTAS) stft_kernel(const
       }
       fft1024_stage1(v, tid, t1, buf1);
     }
-#if AST_STFT_PREFETCH
+#if AST_STFT_PREFETCH == 2
+    {
+      // the 512 samples of this group's next pair that no group of this iteration has touched: lines into L1
+      const int tn = ta + 2 * kStftGroups;
+      if (it + 1 < p.iters && tn >= 2 && (tn + 1) * kHop + kNfft / 2 <= len) {
+        const float* __restrict__ xp = x + (tn * kHop - kNfft / 2 + tid);
+#pragma unroll
+        for (int j = 12; j < 20; ++j) asm volatile("prefetch.global.L1 [%0];" ::"l"(xp + 64 * j));
+      }
+    }
+#elif AST_STFT_PREFETCH
     {
       const int tn = ta + 2 * kStftGroups;   // this group's pair of the next iteration
       have_xv = it + 1 < p.iters && tn >= 2 && (tn + 1) * kHop + kNfft / 2 <= len;
