@@ -74,55 +74,57 @@ __device__ __forceinline__ float2 load_bin(const FrameRows& f, long long plane, 
   return make_float2(re, im);
 }
 
-// The 16 inputs of a thread in two batches of eight: all loads of a batch (32, or 64 in an overlap region) are issued
-// before the first value is used, so a pair costs two global-memory round trips instead of sixteen (ncu: the kernel's
-// dominant stall was the long scoreboard on these loads, one round trip per input).
-template <int N0>
-__device__ __forceinline__ void load_inputs8(float2 (&v)[16], int tid, const FrameRows& fa, const FrameRows& fb,
-                                             long long plane, bool live_b) {
-  float are[8], aim[8], bre[8], bim[8];
-  int kk[8];
+// The 16 inputs of a thread: all loads of a batch are issued before the first value is used (ncu: the kernel's
+// dominant stall is the long scoreboard on these loads, one round trip per batch).  Two batches of eight inputs per
+// pair: 32 loads each, 64 when a frame lies inside a section overlap (second section row to be averaged in).
+template <int N0, int CNT, bool kDup>
+__device__ __forceinline__ void load_inputs(float2 (&v)[16], int tid, const FrameRows& fa, const FrameRows& fb,
+                                            long long plane, bool live_b) {
+  float are[CNT], aim[CNT], bre[CNT], bim[CNT];
+  int kk[CNT];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) kk[i] = (N0 + i) < 8 ? 64 * (N0 + i) + tid : 64 * (16 - (N0 + i)) - tid;
-  // the second section row of an overlap frame is loaded in the same batch (predicated off elsewhere), not after it
-  const bool dup_a = fa.r1 != nullptr, dup_b = live_b && fb.r1 != nullptr;
-  float are1[8], aim1[8], bre1[8], bim1[8];
+  for (int i = 0; i < CNT; ++i) kk[i] = (N0 + i) < 8 ? 64 * (N0 + i) + tid : 64 * (16 - (N0 + i)) - tid;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < CNT; ++i) {
     are[i] = __ldg(fa.r0 + kk[i]);
     aim[i] = __ldg(fa.r0 + plane + kk[i]);
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < CNT; ++i) {
     bre[i] = live_b ? __ldg(fb.r0 + kk[i]) : 0.f;
     bim[i] = live_b ? __ldg(fb.r0 + plane + kk[i]) : 0.f;
   }
+  if (kDup) {
+    // the second section row of an overlap frame is loaded in the same batch (predicated off elsewhere), not after it
+    const bool dup_a = fa.r1 != nullptr, dup_b = live_b && fb.r1 != nullptr;
+    float are1[CNT], aim1[CNT], bre1[CNT], bim1[CNT];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    are1[i] = dup_a ? __ldg(fa.r1 + kk[i]) : 0.f;
-    aim1[i] = dup_a ? __ldg(fa.r1 + plane + kk[i]) : 0.f;
-  }
+    for (int i = 0; i < CNT; ++i) {
+      are1[i] = dup_a ? __ldg(fa.r1 + kk[i]) : 0.f;
+      aim1[i] = dup_a ? __ldg(fa.r1 + plane + kk[i]) : 0.f;
+    }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    bre1[i] = dup_b ? __ldg(fb.r1 + kk[i]) : 0.f;
-    bim1[i] = dup_b ? __ldg(fb.r1 + plane + kk[i]) : 0.f;
-  }
-  if (dup_a) {  // ascending section order like the reference's += loop, then / count (= 2)
+    for (int i = 0; i < CNT; ++i) {
+      bre1[i] = dup_b ? __ldg(fb.r1 + kk[i]) : 0.f;
+      bim1[i] = dup_b ? __ldg(fb.r1 + plane + kk[i]) : 0.f;
+    }
+    if (dup_a) {  // ascending section order like the reference's += loop, then / count (= 2)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      are[i] = (are1[i] + are[i]) * 0.5f;
-      aim[i] = (aim1[i] + aim[i]) * 0.5f;
+      for (int i = 0; i < CNT; ++i) {
+        are[i] = (are1[i] + are[i]) * 0.5f;
+        aim[i] = (aim1[i] + aim[i]) * 0.5f;
+      }
+    }
+    if (dup_b) {
+#pragma unroll
+      for (int i = 0; i < CNT; ++i) {
+        bre[i] = (bre1[i] + bre[i]) * 0.5f;
+        bim[i] = (bim1[i] + bim[i]) * 0.5f;
+      }
     }
   }
-  if (dup_b) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      bre[i] = (bre1[i] + bre[i]) * 0.5f;
-      bim[i] = (bim1[i] + bim[i]) * 0.5f;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < CNT; ++i) {
     float2 xa = make_float2(are[i], aim[i]), xb = make_float2(bre[i], bim[i]);
     if ((N0 + i == 0 || N0 + i == 8) && tid == 0) xa.y = 0.f, xb.y = 0.f;  // self-conjugate bins 0 / 512
     v[N0 + i] = (N0 + i) < 8 ? make_float2(xa.x - xb.y, -(xa.y + xb.x)) : make_float2(xa.x + xb.y, -(xb.x - xa.y));
@@ -179,6 +181,11 @@ __device__ __forceinline__ void emit_segments(const IstftParams& p, const OlaEmi
 // resident CTAs per SM the register allocation is sized for: 8 -> 128 registers, no spills, 0.1355 ms per 64 clips;
 // 10 -> 102 registers, 148 B of spills, 0.1415; 9 -> 0.1405; 12 -> 80 registers, 0.215.  (An L1 prefetch of the next
 // pair's rows after stage 1 made it slower at every occupancy: 0.146 - 0.152.)
+// 1: a pair outside the section overlaps loads its 16 inputs in ONE batch of 64 loads instead of two of 32 (measured:
+// 0.139 vs 0.1357 ms per 64 clips at 8 CTAs per SM - the longer dependency-free prologue costs more than the saved trip)
+#ifndef AST_ISTFT_ONE_BATCH
+#define AST_ISTFT_ONE_BATCH 0
+#endif
 #ifndef AST_ISTFT_CTAS
 #define AST_ISTFT_CTAS 8
 #endif
@@ -226,8 +233,15 @@ __global__ void __launch_bounds__(kIstftThreads, AST_ISTFT_CTAS) istft_kernel(co
       const FrameRows fa = merged_rows(p, clip, t);
       const FrameRows fb = live_b ? merged_rows(p, clip, t + 1) : fa;
       float2 v[16];
-      load_inputs8<0>(v, tid, fa, fb, p.plane, live_b);
-      load_inputs8<8>(v, tid, fa, fb, p.plane, live_b);
+#if AST_ISTFT_ONE_BATCH
+      if (fa.r1 == nullptr && (!live_b || fb.r1 == nullptr)) {
+        load_inputs<0, 16, false>(v, tid, fa, fb, p.plane, live_b);
+      } else
+#endif
+      {
+        load_inputs<0, 8, true>(v, tid, fa, fb, p.plane, live_b);
+        load_inputs<8, 8, true>(v, tid, fa, fb, p.plane, live_b);
+      }
       fft1024_stage1(v, tid, t1, buf1);
     }
     __syncthreads();
