@@ -329,6 +329,10 @@ int launch_stft(const ast_plan* plan, const float* wave, const int32_t* lengths,
   long long iters = (groups_per_clip * batch + slots_total - 1) / slots_total;
   if (iters < 1) iters = 1;
   if (iters > 8) iters = 8;
+  if (const char* env = getenv("AST_STFT_ITERS")) {  // diagnostic override
+    const int v = atoi(env);
+    if (v >= 1 && v <= 64) iters = v;
+  }
   p.iters = (int)iters;
   dim3 grid((unsigned)((groups_per_clip + iters - 1) / iters), (unsigned)batch);
   ProfileSpan span("stft_kernel", st);

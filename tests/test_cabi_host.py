@@ -1,6 +1,7 @@
 """CPU-side checks of the C-ABI library: it loads, exports every symbol the header declares, its
 host-only helpers agree with the oracle, and compute entry points fail loudly without a GPU."""
 import ctypes
+import importlib
 import os
 import re
 
@@ -101,3 +102,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_hostmem_cpulist_parser_and_scoped_binding():
+    # host-side placement helper of the host-buffer API: parser + "never raises, always restores"
+    import os
+
+    hostmem = importlib.import_module("audio_style_transfer_b200.hostmem")
+    assert hostmem._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert hostmem._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    with hostmem.device_local_affinity(0) as info:      # no CUDA device here: must report, not raise
+        assert info["bound"] in (True, False) and "why" in info
+    assert os.sched_getaffinity(0) == before
