@@ -6,7 +6,7 @@
 // The sparsified 12 x 129 FFT basis is folded with the 256-point real DFT into one real
 // 256 x 24 time-domain matrix (identical for every octave up to sqrt(2^i)), which is what the
 // projection kernel contracts against.  The 2:1 decimator is the soxr-HQ-like Kaiser design
-// frozen in DESIGN.md (the checker re-derives both independently: tests/test_plan_constants.py).
+// frozen in DESIGN.md (the checker re-derives both independently: tests/test_cabi_host.py::test_plan_constants_match_oracle).
 #include <algorithm>
 #include <cmath>
 #include <complex>

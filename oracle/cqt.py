@@ -23,7 +23,7 @@ pass-band end ``1 - 0.05 / TO_3dB(rej)`` = 0.9136 x new Nyquist, stop-band begin
 1.0 x new Nyquist, linear phase, ``(bits + 1) * 6.02`` dB = 126.4 dB rejection,
 Kaiser-windowed sinc as in ``lsx_design_lpf`` / ``lsx_make_lpf``) and frozen here as
 ``decimator_taps()``; the CUDA path uses the same taps (``ast_host_decimator_taps``
-in the C-ABI re-derives them; ``tests/test_plan_constants.py`` compares the two).
+in the C-ABI re-derives them; ``tests/test_cabi_host.py::test_plan_constants_match_oracle`` compares the two).
 """
 from __future__ import annotations
 
