@@ -53,6 +53,9 @@ struct StftParams {
 #ifndef AST_STFT_CTAS
 #define AST_STFT_CTAS 4     // resident CTAs per SM the register allocation is sized for
 #endif
+#ifndef AST_STFT_PROLOGUE
+#define AST_STFT_PROLOGUE 1 // 1: 16-byte twiddle copy with all loads in flight + first pair's samples prefetched before it
+#endif
 #ifndef AST_STFT_PREFETCH
 #define AST_STFT_PREFETCH 2 // 1: the next interior pair's 20 samples are loaded right after stage 1 (20 more live registers, spills)
                             // 2: the 512 samples of the next pair that this iteration has not touched are prefetched into the L1
@@ -156,14 +159,41 @@ __global__ void __launch_bounds__(kStftThreads, AST_STFT_CTAS) stft_kernel(const
   const int group = threadIdx.x >> 6, tid = threadIdx.x & 63;
   float2* buf1 = smem + kTw1Size + kTw2Size + group * (kBuf1Size + kBuf2Size);
   float2* buf2 = buf1 + kBuf1Size;
+  const int b = blockIdx.y;
+  const int len = (int)(p.lengths ? p.lengths[b] : p.max_samples);
+#if AST_STFT_PROLOGUE
+  {
+    // the first pair's sample lines start their trip to the L1 before the twiddle tables are copied
+    const int ta0 = 2 * (blockIdx.x * p.iters * kStftGroups + group);
+    if (ta0 >= 2 && (ta0 + 1) * kHop + kNfft / 2 <= len) {
+      const float* xp = p.wave + (long long)b * p.wave_stride + (ta0 * kHop - kNfft / 2 + tid);
+#pragma unroll
+      for (int j = 0; j < 20; ++j) asm volatile("prefetch.global.L1 [%0];" ::"l"(xp + 64 * j));
+    }
+  }
+  {
+    // 10 KB of twiddles as 16-byte loads, all in flight before the first store (the tables are 16-byte aligned)
+    static_assert((kTw1Size + kTw2Size) % (2 * kStftThreads) == 0, "twiddle copy assumes whole rounds");
+    constexpr int kRounds = (kTw1Size + kTw2Size) / (2 * kStftThreads);
+    const float4* __restrict__ src1 = reinterpret_cast<const float4*>(p.t1);
+    const float4* __restrict__ src2 = reinterpret_cast<const float4*>(p.t2);
+    float4 tw[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      const int i = threadIdx.x + r * kStftThreads;   // float4 index into [t1 | t2]
+      tw[r] = i < kTw1Size / 2 ? __ldg(src1 + i) : __ldg(src2 + (i - kTw1Size / 2));
+    }
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) reinterpret_cast<float4*>(smem)[threadIdx.x + r * kStftThreads] = tw[r];
+  }
+#else
   for (int i = threadIdx.x; i < kTw1Size; i += kStftThreads) t1[i] = p.t1[i];
   for (int i = threadIdx.x; i < kTw2Size; i += kStftThreads) t2[i] = p.t2[i];
+#endif
   float win[16];
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1) win[n1] = __ldg(p.hann + 64 * n1 + tid);
 
-  const int b = blockIdx.y;
-  const int len = (int)(p.lengths ? p.lengths[b] : p.max_samples);
   const int frames_b = num_frames(len);
   const int sections_b = p.out.layout == AST_LAYOUT_SECTIONS ? num_sections(frames_b, p.out.window, p.overlap) : 0;
   const float* __restrict__ x = p.wave + (long long)b * p.wave_stride;
