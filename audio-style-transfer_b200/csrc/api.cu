@@ -157,17 +157,26 @@ int ast_features_forward(const ast_plan* plan, const float* wave, const int32_t*
   rc = carve(workspace, workspace_bytes, batch, max_samples, &w);
   if (rc != AST_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const float2* table = nullptr;
-  if (mean) {
-    const int n = 2 * kFTotal * (stats_per_clip ? batch : 1);
-    rc = launch_prep_stats(mean, std_, eps, n, w.stats_table, st);
+  const float2* table = mean ? w.stats_table : nullptr;
+  const int n_stats = mean ? 2 * kFTotal * (stats_per_clip ? batch : 1) : 0;
+  // default path: ONE small kernel prepares the statistics table, the section counts and the decimator's zeroed
+  // completion counters, and the decimator is launched as its programmatic dependent
+  const bool chained = g_overlap_streams && !profile_on() && use_tc_decimator() && use_tc_cqt() && batch > 0;
+  if (chained) {
+    rc = launch_features_prologue(mean, std_, eps, n_stats, w.stats_table, lengths, batch, max_samples, layout, dim1,
+                                  plan->cfg.window_size, plan->cfg.overlap_frames, n_sections, w.dec_flags,
+                                  (int)(decimator_flag_bytes(batch, max_samples) / sizeof(int)), st);
     if (rc != AST_OK) return rc;
-    table = w.stats_table;
-  }
-  if (n_sections) {
-    rc = launch_count_sections(lengths, batch, max_samples, layout, dim1, plan->cfg.window_size, plan->cfg.overlap_frames,
-                               n_sections, st);
-    if (rc != AST_OK) return rc;
+  } else {
+    if (mean) {
+      rc = launch_prep_stats(mean, std_, eps, n_stats, w.stats_table, st);
+      if (rc != AST_OK) return rc;
+    }
+    if (n_sections) {
+      rc = launch_count_sections(lengths, batch, max_samples, layout, dim1, plan->cfg.window_size, plan->cfg.overlap_frames,
+                                 n_sections, st);
+      if (rc != AST_OK) return rc;
+    }
   }
   OutSpec o = make_out(plan, out, layout, dim1, kFTotal, 0);
   o.stats = table;
@@ -188,7 +197,8 @@ int ast_features_forward(const ast_plan* plan, const float* wave, const int32_t*
   // tail, block by block behind its completion counters) -> STFT (never waits: disjoint output columns; its small CTAs
   // fill the SMs as the persistent CQT CTAs retire).  The memset inside launch_decimate_cascade is an ordinary stream
   // operation, so nothing of this call starts before the previous call's kernels have finished.
-  rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, st);
+  rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, st,
+                               /*flags_zeroed=*/chained);
   if (rc == AST_OK)
     rc = launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride,
                     use_tc_decimator() ? w.dec_flags : nullptr, oq, st);

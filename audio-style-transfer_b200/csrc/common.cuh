@@ -174,9 +174,12 @@ int launch_count_sections(const int32_t* lengths, int batch, long long max_sampl
                           int window, int overlap, int32_t* n_out, cudaStream_t st);
 int launch_stft(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
                 long long wave_stride, const OutSpec& out, cudaStream_t st, int pad_zero = 0, bool pdl = false);
+int launch_features_prologue(const float* mean, const float* std_, float eps, int n_stats, float2* table, const int32_t* lengths,
+                             int batch, long long max_samples, int layout, int dim1, int window, int overlap, int32_t* n_out,
+                             int* flags, int n_flags, cudaStream_t st);
 int launch_decimate_cascade(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch,
                             long long max_samples, long long wave_stride, float* ws, long long ws_clip_stride,
-                            int* flags, cudaStream_t st);
+                            int* flags, cudaStream_t st, bool flags_zeroed = false);
 int launch_cqt(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
                long long wave_stride, const float* ws, long long ws_clip_stride, const int* dec_flags, const OutSpec& out,
                cudaStream_t st);
@@ -208,7 +211,7 @@ long long decimator_stage_done_offset(int batch, long long max_samples);  // int
 int decimator_tiles_of_stage(long long max_samples, int stage);            // tiles per clip of a stage
 int launch_decimate_cascade_tc(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch,
                                long long max_samples, long long wave_stride, float* ws, long long ws_clip_stride,
-                               int* flags, cudaStream_t st);
+                               int* flags, cudaStream_t st, bool flags_zeroed = false);
 void set_tc_decimator(int on);
 int istft_init();  // into __constant__ memory of decimate.cu
 

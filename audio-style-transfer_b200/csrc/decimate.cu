@@ -122,11 +122,11 @@ int upload_decimator_taps(const float* taps_scaled) {
 // Runs the six stages: octave buffer i (1..6) of clip b lives at ws + b * ws_clip_stride + octave_offset(i).
 int launch_decimate_cascade(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch,
                             long long max_samples, long long wave_stride, float* ws, long long ws_clip_stride,
-                            int* flags, cudaStream_t st) {
+                            int* flags, cudaStream_t st, bool flags_zeroed) {
   if ((batch > 1 && (wave_stride & 1)) || (reinterpret_cast<uintptr_t>(wave) & 7))
     return fail(AST_ERR_INVALID_ARG, "wave rows must be 8-byte aligned (even stride) for the decimator");
   if (g_use_tc_decimator)
-    return launch_decimate_cascade_tc(plan, wave, lengths, batch, max_samples, wave_stride, ws, ws_clip_stride, flags, st);
+    return launch_decimate_cascade_tc(plan, wave, lengths, batch, max_samples, wave_stride, ws, ws_clip_stride, flags, st, flags_zeroed);
   for (int i = 0; i < kOctaves - 1; ++i) {
     const float* in = i == 0 ? wave : ws + octave_offset(max_samples, i);
     const long long in_stride = i == 0 ? wave_stride : ws_clip_stride;

@@ -282,7 +282,6 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
   unsigned int* stored_count = reinterpret_cast<unsigned int*>(bars + 15);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  pdl_launch_dependents();  // the next stage may start its prologue as soon as SMs free up
   for (int i = tid; i < kStripFloats / 4; i += kThreads) {
     reinterpret_cast<float4*>(t_hi)[i] = __ldg(reinterpret_cast<const float4*>(p.strip_hi) + i);
     reinterpret_cast<float4*>(t_lo)[i] = __ldg(reinterpret_cast<const float4*>(p.strip_lo) + i);
@@ -305,7 +304,11 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
   __syncthreads();
   umma::fence_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();  // everything below reads the previous stage's output / overwrites buffers its predecessors read
+  // The prologue above overlaps the previous kernel of the stream; everything below needs its writes (the zeroed
+  // completion counters).  Dependents (the CQT projection, then the STFT) are released only AFTER the wait, so that
+  // they too start behind the feature call's prologue kernel (statistics table) without waiting for anything themselves.
+  pdl_wait();
+  pdl_launch_dependents();
   const int total = p.tile_prefix[kDecStages];
   int tile = blockIdx.x;
   if (tile < total && !dtc_decode(p, tile).live) tile = dtc_next_live(p, tile, total);
@@ -579,7 +582,7 @@ long long decimator_stage_done_offset(int batch, long long max_samples) {
 // the whole cascade: octave buffer i (1..6) of clip b lives at ws + b * ws_clip_stride + octave_offset(i)
 int launch_decimate_cascade_tc(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch,
                                long long max_samples, long long wave_stride, float* ws, long long ws_clip_stride,
-                               int* flags, cudaStream_t st) {
+                               int* flags, cudaStream_t st, bool flags_zeroed) {
   if (batch == 0) return AST_OK;
   if (!flags) return fail(AST_ERR_WORKSPACE, "the decimator needs its completion-flag region of the workspace");
   DecimateTcParams p;
@@ -608,7 +611,8 @@ int launch_decimate_cascade_tc(const ast_plan* plan, const float* wave, const in
     const char* env = getenv("AST_DEC_DEBUG");
     p.debug = env ? atoi(env) : 0;
   }
-  AST_CUDA_TRY(cudaMemsetAsync(flags, 0, decimator_flag_bytes(batch, max_samples), st));
+  // the fused feature call zeroes the counters in its prologue kernel (this kernel's programmatic primary) instead
+  if (!flags_zeroed) AST_CUDA_TRY(cudaMemsetAsync(flags, 0, decimator_flag_bytes(batch, max_samples), st));
   long long ctas = total;
   if (ctas > plan->sm_count) ctas = plan->sm_count;  // persistent and co-resident: one CTA per SM (tiles wait on each other)
   ProfileSpan span("decimate2_tc_kernel", st);

@@ -379,7 +379,7 @@ def main():
         cpu = cpu_baseline_leg(wave_np, mean, std)
 
     if rank == 0:
-        launches_per_step = 1 + 1 + 1 + 1 + 1  # prep_stats, count_sections, decimate2_tc (six stages), cqt_tc, stft
+        launches_per_step = 1 + 1 + 1 + 1  # features_prologue (stats table, section counts, counters), decimate2_tc (six stages), cqt_tc, stft
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
