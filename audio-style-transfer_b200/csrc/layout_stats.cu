@@ -48,20 +48,35 @@ int launch_count_sections(const int32_t* lengths, int batch, long long max_sampl
 // decimator that follows is a programmatic dependent of this kernel: its prologue (operand strips, TMEM, barriers)
 // overlaps it, and its griddepcontrol.wait - executed BEFORE it releases its own dependents - orders the CQT
 // projection and the STFT behind these writes.
-__global__ void features_prologue_kernel(const float* __restrict__ mean, const float* __restrict__ std_, float eps, int n_stats,
-                                         float2* __restrict__ table, const int32_t* __restrict__ lengths, int batch,
-                                         long long max_samples, int layout, int dim1, int window, int overlap,
-                                         int32_t* __restrict__ n_out, int* __restrict__ flags, int n_flags) {
+struct FeaturesPrologueParams {
+  const float* mean;
+  const float* std_;
+  float eps;
+  int n_stats;
+  float2* table;
+  const int32_t* lengths;
+  int batch;
+  long long max_samples;
+  int layout, dim1, window, overlap;
+  int32_t* n_out;
+  int* flags;
+  int n_flags;
+};
+
+__global__ void features_prologue_kernel(const FeaturesPrologueParams p) {
+  // itself a programmatic dependent of whatever kernel precedes it on the stream (back-to-back feature calls: the
+  // previous call's STFT, which still reads the table this kernel rewrites): launch latency overlaps, the work waits
+  pdl_wait();
   pdl_launch_dependents();  // the decimator's prologue may start; it waits for this grid before it reads the counters
   const int stride = gridDim.x * blockDim.x;
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int i = i0; i < n_flags; i += stride) flags[i] = 0;
-  for (int i = i0; i < n_stats; i += stride) table[i] = make_float2(mean[i], 1.0f / (std_[i] + eps));
-  if (n_out)
-    for (int b = i0; b < batch; b += stride) {
-      const int frames = num_frames(lengths ? lengths[b] : max_samples);
-      int v = layout == AST_LAYOUT_FLAT ? frames : num_sections(frames, window, overlap);
-      n_out[b] = v > dim1 ? dim1 : v;
+  for (int i = i0; i < p.n_flags; i += stride) p.flags[i] = 0;
+  for (int i = i0; i < p.n_stats; i += stride) p.table[i] = make_float2(p.mean[i], 1.0f / (p.std_[i] + p.eps));
+  if (p.n_out)
+    for (int b = i0; b < p.batch; b += stride) {
+      const int frames = num_frames(p.lengths ? p.lengths[b] : p.max_samples);
+      int v = p.layout == AST_LAYOUT_FLAT ? frames : num_sections(frames, p.window, p.overlap);
+      p.n_out[b] = v > p.dim1 ? p.dim1 : v;
     }
 }
 
@@ -73,10 +88,10 @@ int launch_features_prologue(const float* mean, const float* std_, float eps, in
   if (work == 0) return AST_OK;
   int ctas = (work + 255) / 256;
   if (ctas > 1184) ctas = 1184;
+  const FeaturesPrologueParams p{mean, std_, eps, n_stats, table, lengths, batch, max_samples, layout, dim1, window, overlap,
+                                 n_out, flags, n_flags};
   ProfileSpan span("features_prologue_kernel", st);
-  features_prologue_kernel<<<ctas, 256, 0, st>>>(mean, std_, eps, n_stats, table, lengths, batch, max_samples, layout, dim1,
-                                                 window, overlap, n_out, flags, n_flags);
-  AST_LAUNCH_CHECK("features_prologue_kernel");
+  AST_CUDA_TRY(launch_with_pdl(features_prologue_kernel, dim3((unsigned)ctas), 256, 0, st, p));
   return AST_OK;
 }
 
