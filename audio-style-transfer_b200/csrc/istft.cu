@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(kIstftThreads, AST_ISTFT_CTAS) istft_kernel(co
   float2* buf1 = smem;
   float2* buf2 = buf1 + kBuf1Size;
   const int tid = threadIdx.x;
+  pdl_launch_dependents();  // a programmatic dependent launched next may run its prologue; an ordinary launch still waits
 
   const int b = blockIdx.y;
   const float* __restrict__ clip = p.spec + (long long)b * p.clip_stride;
@@ -223,6 +224,9 @@ __global__ void __launch_bounds__(kIstftThreads, AST_ISTFT_CTAS) istft_kernel(co
   for (int s = 0; s < 4; ++s)
 #pragma unroll
     for (int c = 0; c < 5; ++c) ola.acc[s][c] = 0.f;
+  // launched with programmatic stream serialisation: everything above (plan constants only) overlaps the tail of the
+  // previous kernel on the stream; the spectrogram it may have produced and the output buffer are touched only below
+  pdl_wait();
   __syncthreads();
 
   // frames g0 - 3 .. g1 - 1 contribute; pairs start on the even frame g0 - 4 (g0 is even)
@@ -313,8 +317,7 @@ int launch_istft(const ast_plan* plan, const float* spec, int batch, int dim1, i
   p.run_segs = best_r;
   dim3 grid((unsigned)((segs + best_r - 1) / best_r), (unsigned)batch);
   ProfileSpan span("istft_kernel", st);
-  istft_kernel<<<grid, kIstftThreads, kIstftSmem, st>>>(p);
-  AST_LAUNCH_CHECK("istft_kernel");
+  AST_CUDA_TRY(launch_with_pdl(istft_kernel, grid, kIstftThreads, kIstftSmem, st, p));
   return AST_OK;
 }
 
