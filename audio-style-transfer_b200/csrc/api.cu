@@ -53,7 +53,9 @@ static size_t octave_bytes(int batch, long long max_samples) {
   return align_up(sizeof(float) * (size_t)cqt_ws_clip_stride(max_samples) * (size_t)batch);
 }
 
-static size_t flag_bytes(int batch, long long max_samples) { return align_up(decimator_flag_bytes(batch, max_samples)); }
+// the decimator's completion counters + one more int: the STFT's finished-CTA counter of the chained feature call
+static size_t flag_bytes(int batch, long long max_samples) { return align_up(decimator_flag_bytes(batch, max_samples) + sizeof(int)); }
+static int tail_counter_index(int batch, long long max_samples) { return (int)((decimator_flag_bytes(batch, max_samples) + 3) / 4); }
 
 static int carve(void* ws, size_t ws_bytes, int batch, long long max_samples, Workspace* w) {
   const size_t need = stats_table_bytes(batch) + octave_bytes(batch, max_samples) + flag_bytes(batch, max_samples);
@@ -165,7 +167,7 @@ int ast_features_forward(const ast_plan* plan, const float* wave, const int32_t*
   if (chained) {
     rc = launch_features_prologue(mean, std_, eps, n_stats, w.stats_table, lengths, batch, max_samples, layout, dim1,
                                   plan->cfg.window_size, plan->cfg.overlap_frames, n_sections, w.dec_flags,
-                                  (int)(decimator_flag_bytes(batch, max_samples) / sizeof(int)), st);
+                                  tail_counter_index(batch, max_samples) + 1, st);
     if (rc != AST_OK) return rc;
   } else {
     if (mean) {
@@ -203,7 +205,11 @@ int ast_features_forward(const ast_plan* plan, const float* wave, const int32_t*
     rc = launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride,
                     use_tc_decimator() ? w.dec_flags : nullptr, oq, st);
   if (rc != AST_OK) return rc;
-  return launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st, 0, /*pdl=*/use_tc_decimator() && use_tc_cqt());
+  // the STFT never waits for the CQT projection it is a programmatic dependent of, so it could finish first; its last
+  // CTA to finish then waits for that grid (tail counter), so that "the call's last kernel is complete" means the whole
+  // call is complete - which a following programmatic dependent (the next call's prologue, the iSTFT) relies on
+  return launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st, 0, /*pdl=*/chained,
+                     chained ? reinterpret_cast<unsigned int*>(w.dec_flags + tail_counter_index(batch, max_samples)) : nullptr);
 }
 
 int ast_istft_forward(const ast_plan* plan, const float* spec, int32_t batch, int32_t dim1, int32_t f_in, int32_t layout,

@@ -173,7 +173,8 @@ int launch_prep_stats(const float* mean, const float* std, float eps, int n, flo
 int launch_count_sections(const int32_t* lengths, int batch, long long max_samples, int layout, int dim1,
                           int window, int overlap, int32_t* n_out, cudaStream_t st);
 int launch_stft(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
-                long long wave_stride, const OutSpec& out, cudaStream_t st, int pad_zero = 0, bool pdl = false);
+                long long wave_stride, const OutSpec& out, cudaStream_t st, int pad_zero = 0, bool pdl = false,
+                unsigned int* tail_counter = nullptr);
 int launch_features_prologue(const float* mean, const float* std_, float eps, int n_stats, float2* table, const int32_t* lengths,
                              int batch, long long max_samples, int layout, int dim1, int window, int overlap, int32_t* n_out,
                              int* flags, int n_flags, cudaStream_t st);

@@ -40,6 +40,7 @@ struct StftParams {
   const float* hann;
   int overlap;
   int debug;            // diagnostic (AST_STFT_DEBUG): 1 stores suppressed (only k == 1000000 would store)
+  unsigned int* tail_counter;  // chained feature call: finished-CTA counter (zeroed by the prologue kernel), else nullptr
   int pad_zero;         // 0: reflect padding (torch.stft, get_STFT); 1: zero padding (librosa.stft default, mse_spectrogram)
   OutSpec out;
 };
@@ -320,6 +321,16 @@ __global__ void __launch_bounds__(kStftThreads, AST_STFT_CTAS) stft_kernel(const
       }
     }
   }
+  if (p.tail_counter) {
+    // This grid never waited for its programmatic primary (the CQT projection) and may finish before it.  The last CTA
+    // to get here waits for that grid, so the STFT - the feature call's last kernel - cannot COMPLETE before the call's
+    // other kernels have: a following programmatic dependent that waits for "the previous kernel" gets the whole call.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int done = atomicAdd(p.tail_counter, 1u);
+      if (done == gridDim.x * gridDim.y - 1) pdl_wait();
+    }
+  }
 }
 
 static int g_stft_ctas_per_sm = 2;
@@ -333,9 +344,10 @@ int stft_init() {
 }
 
 int launch_stft(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
-                long long wave_stride, const OutSpec& out, cudaStream_t st, int pad_zero, bool pdl) {
+                long long wave_stride, const OutSpec& out, cudaStream_t st, int pad_zero, bool pdl, unsigned int* tail_counter) {
   StftParams p;
   p.pad_zero = pad_zero;
+  p.tail_counter = pdl ? tail_counter : nullptr;
   {
     const char* env = getenv("AST_STFT_DEBUG");
     p.debug = env ? atoi(env) : 0;

@@ -226,6 +226,38 @@ def test_cqt_batch_shapes_exercise_the_decimator_tile_scheduler(fe, batch, n):
     assert np.abs(out[batch - 1].cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("batch", [1, 2, 9])
+def test_back_to_back_calls_share_a_workspace_safely(fe, piano_stats, batch):
+    """The feature call is a chain of programmatic dependent launches (prologue -> decimator -> CQT projection -> STFT)
+    whose next call starts behind "the previous kernel" only; with few clips the STFT finishes long before the CQT
+    projection, so this is the case where a missing ordering would let call k + 1 rewrite the statistics table / zero the
+    completion counters under call k.  40 un-synchronised calls on alternating inputs (and an iSTFT straight after a
+    feature call) must equal the same calls made one at a time."""
+    mean, std = piano_stats
+    mean_d, std_d = torch.from_numpy(mean).cuda(), torch.from_numpy(std).cuda()
+    n = 60000
+    xs = [cuda(np.stack([synth.clip("piano" if (i + j) % 2 else "violin", 300 + 7 * j + i, n) for i in range(batch)]))
+          for j in range(2)]
+    refs = []
+    for x in xs:
+        sec, counts = fe.features(x, mean=mean_d, std=std_d, layout="sections")
+        torch.cuda.synchronize()
+        refs.append((sec.clone(), counts.clone()))
+    outs = []
+    for k in range(40):
+        sec, counts = fe.features(xs[k % 2], mean=mean_d if k % 3 else mean_d * 1.0, std=std_d, layout="sections")
+        if k >= 38:
+            outs.append((k % 2, sec, counts))
+        else:
+            y = fe.istft(sec, layout="sections", overlap=96)      # reads the STFT columns of the call just enqueued
+    torch.cuda.synchronize()
+    for which, sec, counts in outs:
+        assert torch.equal(sec, refs[which][0]) and torch.equal(counts, refs[which][1])
+    y_ref = fe.istft(refs[1][0], layout="sections", overlap=96)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref)
+
+
 def test_per_clip_statistics_and_batcher(fe, dl, piano_stats):
     import os
     from conftest import GOLDEN
