@@ -1,5 +1,6 @@
 #!/bin/bash
-# One GPU call: tests, default bench (both arms), ncu launch list, ncu --set full of the four hot kernels.
+# Tests, default bench (both arms), ncu launch list, ncu --set full of the hot kernels.  One ncu pass per GPU call: run the
+# blocks below as four separate calls (each ncu pass only after the same command has run plain).
 set -x
 python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/pytest_gpu.log
 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
