@@ -556,6 +556,11 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
   umma::fence_before_thread_sync();
   __syncthreads();
   if (warp == kMmaWarp) umma::tmem_dealloc(tmem_base, kTmemCols);
+  // The projection has consumed every decimator tile, but the decimator's publisher bumps a tile's flag BEFORE its
+  // stage counter: formally that grid may still be executing its last atomicAdd.  Each CTA therefore waits for its
+  // programmatic primary before it exits, so "the CQT grid is complete" implies "the decimator grid is complete" -
+  // which is what the STFT's tail wait, and through it the next call's counter-zeroing prologue, relies on.
+  if (p.flags && tid == 0) pdl_wait();
 }
 
 // host: B image.  kmat[n][24] (double) -> [ks 32][c 2][j 64: hi 0..31 then lo 32..63][kk 4], n = 8 ks + 4 c + kk

@@ -150,10 +150,31 @@ def _list_audio(directory: str):
     return sorted(os.path.join(directory, f) for f in os.listdir(directory) if f.endswith(".mp3") or f.endswith(".wav"))
 
 
-def load_clips(paths: Sequence[str], fe: FrontEnd, sample_rate: int = SAMPLE_RATE, cut_time_seconds: float = 10) -> torch.Tensor:
+def load_clips(paths: Sequence[str], fe: FrontEnd, sample_rate: int = SAMPLE_RATE, cut_time_seconds: float = 10,
+               skip_errors: bool = False):
     """``load_audio`` for a list of files -> ``(len(paths), L')`` float32 on the device.  Files are decoded on the
-    host and grouped by (channels, rate) so that each group is ONE device call (pad / cut + resample + mono mix)."""
-    decoded = [_decode_file(p) for p in paths]
+    host and grouped by (channels, rate) so that each group is ONE device call (pad / cut + resample + mono mix).
+
+    ``skip_errors=True`` is the statistics scripts' behaviour (``compute_separated_stats.py:21-38`` catches per-file
+    errors, prints them and leaves the file out of the count): undecodable files are reported and dropped, and the
+    return value is ``(clips or None, kept_paths)``."""
+    if skip_errors:
+        decoded, kept = [], []
+        for p in paths:
+            try:
+                decoded.append(_decode_file(p))
+                kept.append(p)
+            except Exception as e:  # the reference prints and carries on with the next file
+                print(f"Errore con {p}: {e}")
+        if not kept:
+            return None, []
+        return load_clips_decoded(decoded, fe, sample_rate, cut_time_seconds), kept
+    return load_clips_decoded([_decode_file(p) for p in paths], fe, sample_rate, cut_time_seconds)
+
+
+def load_clips_decoded(decoded, fe: FrontEnd, sample_rate: int = SAMPLE_RATE, cut_time_seconds: float = 10) -> torch.Tensor:
+    """The device part of :func:`load_clips` for already decoded ``(waveform (C, n), rate)`` pairs."""
+    paths = decoded
     out = None
     groups = {}
     for i, (w, sr) in enumerate(decoded):
@@ -218,7 +239,18 @@ class GpuDataLoader:
 
     def __iter__(self):
         n = len(self.dataset)
-        order = torch.randperm(n, generator=self.generator).tolist() if self.shuffle else list(range(n))
+        if self.shuffle:
+            # What DataLoader(shuffle=True).__iter__ does with the global RNG (dataloader.py:172): one draw for the
+            # iterator's base seed, then RandomSampler seeds a fresh generator from a second draw - so the shuffle
+            # order under torch.manual_seed(s) equals the reference DataLoader's (tests/test_cabi_host.py)
+            gen = self.generator
+            if gen is None:
+                torch.empty((), dtype=torch.int64).random_()
+                gen = torch.Generator()
+                gen.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
+            order = torch.randperm(n, generator=gen).tolist()
+        else:
+            order = list(range(n))
         half = self.batch_size // 2
         for k in range(len(self)):
             items = order[k * self.batch_size: k * self.batch_size + half]

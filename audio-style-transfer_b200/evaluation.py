@@ -72,16 +72,18 @@ def instrumentation_similarity(audio1, audio2, sr=22050):
     return float(instrumentation_similarity_device(audio1, audio2).item())
 
 
-def reconstruct_audio_from_sections(sections_tensor):
-    """``evaluation_reconstruction.reconstruct_audio_from_sections`` (``:161-189``): ``(1, S, 2, 287, 513)`` ->
-    the inverse STFT of section 0 as a NumPy array; ``np.zeros(22050)`` on any exception."""
+def reconstruct_audio_from_sections(stft_sections, batch_idx=None, sample_idx=None):
+    """``evaluation_reconstruction.reconstruct_audio_from_sections`` (``:161-189``), same three positional arguments
+    as its call sites (``:345-350``): ``stft_sections (1, S, 2, 287, 513)`` -> the inverse STFT of section 0 as a NumPy
+    array; on any exception the message (with the batch / sample indices, as the reference prints them) and
+    ``np.zeros(22050)``."""
     try:
-        first = sections_tensor[0, 0]
+        first = stft_sections[0, 0]
         if first.shape[-1] != F_STFT:
             raise RuntimeError(f"expected {F_STFT} frequency bins, got {first.shape[-1]}")
         fe = default_frontend(_cuda_device(first))
         audio = fe.istft(first.unsqueeze(0), layout="flat")[0]
         return audio.cpu().numpy()
     except Exception as e:
-        print(f"⚠️ Error in audio reconstruction: {e}")
+        print(f"⚠️ Error in audio reconstruction (batch {batch_idx}, sample {sample_idx}): {e}")
         return np.zeros(22050)

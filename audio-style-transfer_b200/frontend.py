@@ -230,9 +230,15 @@ class FrontEnd:
     def features_host(self, host_wave: torch.Tensor, host_out: torch.Tensor, mean: Optional[torch.Tensor] = None,
                       std: Optional[torch.Tensor] = None, eps: float = 1e-8, chunk: int = 16, n_streams: int = 3) -> torch.Tensor:
         """The host-buffer form of :meth:`features` (sections layout): ``host_wave (B, L)`` float32 in (pinned) host
-        memory -> ``host_out (B, S, 2, 287, 597)`` float32 in (pinned) host memory.  Clips are cut into chunks and
-        H2D copy, kernels and D2H copy of successive chunks overlap on ``n_streams`` CUDA streams (PCIe is full
-        duplex), each with its own device buffers and scratch.  Returns ``host_out`` after everything has landed."""
+        memory -> ``host_out (B, S, 2, 287, 597)`` float32 in (pinned) host memory.  Clips are cut into chunks; the
+        H2D copy of chunk k + 1, the kernels of chunk k and the D2H copy of chunk k - 1 overlap (PCIe is full duplex).
+
+        ALL kernels run on ONE compute stream (the caller's current stream); only the copies run on two side streams,
+        ordered by events, over ``n_streams`` rotating device buffers.  The feature call's tensor-core kernels are
+        persistent grids whose CTAs wait on counters written by other CTAs of the same call (``csrc/decimate_tc.cu``,
+        ``csrc/cqt_tc.cu``): two such calls in flight on different streams could each be partly resident and starve one
+        another, so at most one feature call per device is ever in flight (``include/ast_frontend.h``).  The kernels
+        fill the GPU on their own, so nothing is lost.  Returns ``host_out`` after everything has landed."""
         if host_wave.ndim != 2 or host_wave.dtype != torch.float32 or host_wave.is_cuda:
             raise ValueError("host_wave must be a (B, L) float32 host tensor")
         B, L = host_wave.shape
@@ -244,34 +250,53 @@ class FrontEnd:
         if mean is not None:
             mean = mean.to(device=self.device, dtype=torch.float32).contiguous()
             std = std.to(device=self.device, dtype=torch.float32).contiguous()
-        key = (chunk, L, S, int(n_streams))
+        n_slots = max(2, int(n_streams))
+        key = (chunk, L, S, n_slots)
         pipe = getattr(self, "_pipe", None)
         if pipe is None or pipe["key"] != key:
             with torch.cuda.device(self.device):
-                pipe = {"key": key, "slots": [{
-                    "stream": torch.cuda.Stream(device=self.device),
-                    "x": torch.empty((chunk, L + (L % 2)), dtype=torch.float32, device=self.device),
-                    "y": torch.empty((chunk,) + shape[1:], dtype=torch.float32, device=self.device),
-                    "ws": torch.empty(self.workspace_bytes(chunk, L), dtype=torch.uint8, device=self.device),
-                } for _ in range(int(n_streams))]}
+                pipe = {"key": key,
+                        "h2d": torch.cuda.Stream(device=self.device), "d2h": torch.cuda.Stream(device=self.device),
+                        # one scratch buffer: the compute stream serialises the feature calls that use it
+                        "ws": torch.empty(self.workspace_bytes(chunk, L), dtype=torch.uint8, device=self.device),
+                        "slots": [{
+                            "x": torch.empty((chunk, L + (L % 2)), dtype=torch.float32, device=self.device),
+                            "y": torch.empty((chunk,) + shape[1:], dtype=torch.float32, device=self.device),
+                            "x_free": None,   # event: the kernels that read x have finished
+                            "y_free": None,   # event: the D2H copy that read y has finished
+                        } for _ in range(n_slots)]}
             self._pipe = pipe
         cur = torch.cuda.current_stream(self.device)
+        h2d, d2h = pipe["h2d"], pipe["d2h"]
+        h2d.wait_stream(cur)
+        d2h.wait_stream(cur)
         for slot in pipe["slots"]:
-            slot["stream"].wait_stream(cur)
+            slot["x_free"] = slot["y_free"] = None
         for i, lo in enumerate(range(0, B, chunk)):
             hi = min(lo + chunk, B)
             n = hi - lo
-            slot = pipe["slots"][i % len(pipe["slots"])]
-            with torch.cuda.stream(slot["stream"]):
-                x = slot["x"][:n, :L]
+            slot = pipe["slots"][i % n_slots]
+            x = slot["x"][:n, :L]
+            with torch.cuda.stream(h2d):
+                if slot["x_free"] is not None:
+                    h2d.wait_event(slot["x_free"])
                 x.copy_(host_wave[lo:hi], non_blocking=True)
-                m, sd = mean, std
-                if mean is not None and mean.ndim == 3:
-                    m, sd = mean[lo:hi], std[lo:hi]
-                y, _ = self.features(x, mean=m, std=sd, eps=eps, layout="sections", out=slot["y"][:n], workspace=slot["ws"])
+                x_ready = h2d.record_event()
+            cur.wait_event(x_ready)
+            if slot["y_free"] is not None:
+                cur.wait_event(slot["y_free"])
+            m, sd = mean, std
+            if mean is not None and mean.ndim == 3:
+                m, sd = mean[lo:hi], std[lo:hi]
+            y, _ = self.features(x, mean=m, std=sd, eps=eps, layout="sections", out=slot["y"][:n], workspace=pipe["ws"])
+            y_ready = cur.record_event()
+            slot["x_free"] = y_ready
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(y_ready)
                 host_out[lo:hi].copy_(y, non_blocking=True)
-        for slot in pipe["slots"]:
-            cur.wait_stream(slot["stream"])
+                slot["y_free"] = d2h.record_event()
+        cur.wait_stream(d2h)
+        cur.wait_stream(h2d)
         cur.synchronize()
         return host_out
 

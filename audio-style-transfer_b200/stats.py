@@ -128,10 +128,31 @@ def main(argv=None) -> int:
         for g, files in enumerate(lists):
             mine = [files[i] for i in shard_range(len(files), rank, world)]
             for k in range(0, len(mine), args.batch):
-                wave = load_clips(mine[k: k + args.batch], fe)
+                # per-file errors are printed and the file is left out of the count (compute_separated_stats.py:21-38)
+                wave, kept = load_clips(mine[k: k + args.batch], fe, skip_errors=True)
+                if wave is None:
+                    continue
                 yield wave, torch.full((wave.shape[0],), g, dtype=torch.int32, device=fe.device)
 
-    acc, counts = compute_stats(fe, batches(), n_groups=2)
+    # every rank must reach the all-reduce, whatever happened to its shard: a rank that raised before the collective
+    # would leave the others hanging in NCCL.  A failed rank contributes zeros and the error is re-raised afterwards.
+    error = None
+    acc, counts = fe.new_stats_accumulator(2)
+    try:
+        for wave, gids in batches():
+            fe.stats_accumulate(wave, acc, counts, group_ids=gids)
+    except Exception as e:  # noqa: BLE001 - reported below, after the collective
+        error = e
+        acc.zero_()
+        counts.zero_()
+    failed = torch.tensor([1.0 if error is not None else 0.0], dtype=torch.float64, device=fe.device)
+    allreduce_accumulators(acc, counts)
+    if world > 1:
+        dist.all_reduce(failed)
+    if float(failed[0]) > 0:
+        if world > 1:
+            dist.destroy_process_group()
+        raise RuntimeError(f"statistics pass failed on {int(failed[0])} rank(s)") from error
     if rank == 0:
         paths = write_reference_npz(args.out_dir, finalize_all(acc, counts))
         for key, path in paths.items():

@@ -15,6 +15,12 @@
  *   - all work is enqueued on the caller's stream (cudaStream_t passed as void*), no
  *     internal synchronisation; a plan is immutable after creation and may be used from
  *     several host threads on different streams;
+ *   - EXCEPT: at most ONE ast_features_forward / ast_cqt_forward / ast_stats_accumulate call
+ *     may be in flight per device at a time (issue them on one stream, or order streams with
+ *     events).  Their tensor-core kernels are persistent grids whose CTAs wait on completion
+ *     counters written by other CTAs of the same call; two such grids dispatched interleaved
+ *     from different streams could each be partly resident and starve one another (the
+ *     bounded waits would then trap).  Copies and every other entry point may overlap freely;
  *   - float32 data, int32 lengths, row-major contiguous tensors in the reference's layouts.
  *
  * Geometry (fixed by the reference's call sites, utilityFunctions.py:12,39,62):

@@ -115,3 +115,27 @@ def test_hostmem_cpulist_parser_and_scoped_binding():
     with hostmem.device_local_affinity(0) as info:      # no CUDA device here: must report, not raise
         assert info["bound"] in (True, False) and "why" in info
     assert os.sched_getaffinity(0) == before
+
+
+def test_loader_shuffle_order_equals_torch_dataloader():
+    """GpuDataLoader draws its permutation exactly as DataLoader(shuffle=True) + RandomSampler do under the same
+    torch.manual_seed (the reference's get_dataloader, dataloader.py:172): no file is touched here, only the order."""
+    import torch
+    from torch.utils.data import DataLoader
+
+    dl = importlib.import_module("audio_style_transfer_b200.dataloader")
+
+    class _Waves:
+        batcher = staticmethod(lambda p, v: (p, v))
+
+        def __len__(self):
+            return 12
+
+        def waves(self, items):
+            return list(items), list(items)
+
+    torch.manual_seed(11)
+    want = [int(x) for b in DataLoader(list(range(12)), batch_size=4, shuffle=True, drop_last=True) for x in b[:2]]
+    torch.manual_seed(11)
+    got = [i for p, _ in dl.GpuDataLoader(_Waves(), 4, True) for i in p]
+    assert got == want

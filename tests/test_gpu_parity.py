@@ -380,6 +380,10 @@ def test_small_operators_match_reference_golden(fe, uf, dl, golden, piano_stats)
 
 
 # ------------------------------------------------------------------------------- stats (a10)
+# std relative error <= 1e-5 (the golden is the reference's own float32 compute_stats)
+STD_RTOL = 1e-5
+
+
 def test_stats_match_reference_golden(fe, golden):
     g = golden("stats.npz")
     acc, counts = fe.new_stats_accumulator(1)
@@ -392,7 +396,11 @@ def test_stats_match_reference_golden(fe, golden):
     ref_mean, ref_std = g["mean"], g["std"]
     assert np.all(np.abs(mean - ref_mean) <= 1e-6 + 1e-4 * np.abs(ref_mean))
     nz = ref_std > 0
-    assert np.all(np.abs(std[nz] - ref_std[nz]) <= 2e-5 * ref_std[nz])
+    rel = np.abs(std[nz] - ref_std[nz]) / ref_std[nz]
+    print(f"stats vs the reference's compute_stats: std rel err max {rel.max():.2e} (STFT columns "
+          f"{(np.abs(std[:, :513] - ref_std[:, :513])[nz[:, :513]] / ref_std[:, :513][nz[:, :513]]).max():.2e}), "
+          f"mean abs err max {np.abs(mean - ref_mean).max():.2e}")
+    assert np.all(rel <= STD_RTOL)
     assert np.all(std[~nz] == 0)
     # per-instrument groups + unified = sum of the groups (compute_unified_stats.py walks both trees)
     acc2, counts2 = fe.new_stats_accumulator(2)
@@ -403,7 +411,7 @@ def test_stats_match_reference_golden(fe, golden):
     m0, s0 = stats.finalize(acc2[0], counts2[0])
     assert np.all(np.abs(m0 - o_mean) <= 1e-6 + 1e-4 * np.abs(o_mean))
     nz = o_std > 0
-    assert np.all(np.abs(s0[nz] - o_std[nz]) <= 2e-5 * o_std[nz])
+    assert np.all(np.abs(s0[nz] - o_std[nz]) <= STD_RTOL * o_std[nz])
 
 
 def test_stats_ragged_and_constant(fe):
@@ -460,6 +468,39 @@ def test_full_batch_properties(fe, piano_stats):
     assert float((10 * torch.log10(sig / err)).min()) >= 120.0
 
 
+def test_full_batch_against_oracle(fe, piano_stats):
+    """BASELINE configs[1] at full size AGAINST THE ORACLE: 64 x 10 s clips built from 4 distinct clips (2 piano-like,
+    2 violin-like) at 64 different gains.  STFT and CQT are linear, so the fp64 oracle of clip i is gain_i x the oracle
+    of its base clip; every one of the 64 x (4, 2, 287, 597) outputs is compared, raw and normalised."""
+    mean, std = piano_stats
+    base = synth.batch(4, first_id=40)
+    gains = np.random.default_rng(9).uniform(0.6, 1.6, 64).astype(np.float32)
+    wave = np.tile(base, (16, 1)) * gains[:, None]
+    raw_ref = []
+    for i in range(4):
+        V = oc.cqt(base[i])
+        raw_ref.append(np.concatenate([osp.get_STFT(base[i], dtype=np.float64), np.stack([V.real.T, V.imag.T])], axis=2))
+    raw, counts = fe.features(cuda(wave), layout="sections")
+    nrm, _ = fe.features(cuda(wave), mean=cuda(mean), std=cuda(std), layout="sections")
+    assert counts.tolist() == [4] * 64
+    raw, nrm = raw.cpu().numpy(), nrm.cpu().numpy()
+    worst_s = worst_c = 0.0
+    for i in range(64):
+        # the clip really fed to the kernels is float32(base * gain): its oracle differs from gain x oracle(base) by
+        # the rounding of the product, <= 2^-24 relative per sample - far below the 1e-5 bound
+        ref = raw_ref[i % 4] * float(gains[i])
+        sx, sv = np.abs(ref[..., :513]).max(), np.abs(ref[..., 513:]).max()
+        for s in range(4):
+            seg = ref[:, s * 191 : s * 191 + 287]
+            worst_s = max(worst_s, np.abs(raw[i, s][..., :513] - seg[..., :513]).max() / sx)
+            worst_c = max(worst_c, np.abs(raw[i, s][..., 513:] - seg[..., 513:]).max() / sv)
+            if i % 8 == 3:  # the normalised tensor of every 8th clip, all sections
+                _check_normalised(nrm[i, s][..., :513], seg[..., :513], mean[:, :513], std[:, :513], 1e-5 * sx)
+                _check_normalised(nrm[i, s][..., 513:], seg[..., 513:], mean[:, 513:], std[:, 513:], 1e-5 * sv)
+    print(f"full batch vs oracle: STFT {worst_s:.2e}, CQT {worst_c:.2e} of max")
+    assert worst_s <= 1e-5 and worst_c <= 1e-5, (worst_s, worst_c)
+
+
 def test_features_host_pipeline_equals_device_call(fe, piano_stats):
     """The host-buffer API (chunked H2D / kernels / D2H over several streams) returns exactly what the
     device-resident call returns, for chunk sizes that do and do not divide the batch."""
@@ -474,6 +515,25 @@ def test_features_host_pipeline_equals_device_call(fe, piano_stats):
         assert got is host_out and torch.equal(host_out, ref.cpu()), chunk
     with pytest.raises(ValueError):
         fe.features_host(wave, torch.empty(1, 2, 3))
+
+
+def test_features_host_full_size_chunks_repeatedly(fe, piano_stats):
+    """The persistent tensor-core grids of a feature call wait on counters written by their own CTAs, so two feature
+    calls must never be in flight at once (include/ast_frontend.h).  features_host therefore issues every kernel on ONE
+    stream and only the copies on side streams: 50 passes over 64 full-length clips in chunks of 16 (each chunk's grids
+    are 148 CTAs wide, as in the bench) over 3 rotating buffers must finish and reproduce the device-resident call."""
+    mean, std = piano_stats
+    wave = torch.from_numpy(np.tile(synth.batch(4, first_id=8), (16, 1)))
+    ref, _ = fe.features(wave.cuda(), mean=cuda(mean), std=cuda(std))
+    ref = ref.cpu()
+    host_in = wave.pin_memory()
+    host_out = torch.empty(tuple(ref.shape), dtype=torch.float32).pin_memory()
+    for it in range(50):
+        if it % 10 == 0:
+            host_out.zero_()
+        fe.features_host(host_in, host_out, mean=cuda(mean), std=cuda(std), chunk=16, n_streams=3)
+        if it % 10 == 0 or it == 49:
+            assert torch.equal(host_out, ref), it
 
 
 @pytest.mark.parametrize("env", [{"AST_DECIMATOR": "fma"}, {"AST_CQT": "fma"}, {"AST_DECIMATOR": "fma", "AST_CQT": "fma"},

@@ -62,7 +62,8 @@ def test_gpu_reconstruct_audio_from_sections_mirror():
 
     rng = np.random.default_rng(0)
     sec = rng.standard_normal((1, 4, 2, 287, 513)).astype(np.float32)
-    y = ev.reconstruct_audio_from_sections(torch.from_numpy(sec))
+    y = ev.reconstruct_audio_from_sections(torch.from_numpy(sec), 0, 3)   # three positional arguments, as evaluation_reconstruction.py:345-350 calls it
+    assert np.array_equal(y, ev.reconstruct_audio_from_sections(torch.from_numpy(sec)))
     ref = osp.reconstruct_audio_from_sections(sec)
     assert y.shape == ref.shape == (73216,) and np.abs(y - ref).max() <= 2e-5
     bad = ev.reconstruct_audio_from_sections(torch.zeros(1, 4, 2, 287, 100))   # wrong bin count -> the reference's fallback
