@@ -80,6 +80,7 @@ SIGNATURES = {
     "ast_instrumentation_similarity_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int64]),
     "ast_instrumentation_similarity": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_size_t, c_void_p,
                                                 c_void_p]),
+    "ast_synth_clips": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int64, c_int64, c_void_p]),
     "ast_profile_enable": (c_int, [c_int32]),
     "ast_profile_collect": (c_int, [c_char_p, POINTER(c_float), POINTER(c_int32), c_int32, POINTER(c_int32)]),
 }

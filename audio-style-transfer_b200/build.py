@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libast_frontend.so")
 STAMP_PATH = os.path.join(PKG_DIR, "libast_frontend.stamp")
-SOURCES = ["plan.cu", "stft.cu", "decimate.cu", "decimate_tc.cu", "cqt.cu", "cqt_tc.cu", "istft.cu", "layout_stats.cu", "resample.cu", "metrics.cu", "api.cu"]
+SOURCES = ["plan.cu", "stft.cu", "decimate.cu", "decimate_tc.cu", "cqt.cu", "cqt_tc.cu", "istft.cu", "layout_stats.cu", "resample.cu", "metrics.cu", "synth.cu", "api.cu"]
 HEADERS = ["common.cuh", "fft_core.h", "umma.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -145,6 +145,25 @@ class FrontEnd:
                                                        _stream_ptr(self.device)))
         return out[0:1] if squeeze else out
 
+    # ------------------------------------------------------------------ synthetic dataset-scale input (configs[3])
+    def synth_clips(self, n_clips: int, first_clip_id: int = 0, violin_from_id: int = 1 << 62,
+                    n_samples: int = 220500, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``(n_clips, n_samples)`` float32 on the device: clip ``first_clip_id + b`` of the counter-based synthetic
+        dataset (``ast_synth_clips``: piano-like below ``violin_from_id``, violin-like from there on).  A pure function of
+        the clip id, so any rank regenerates any shard bit for bit."""
+        if out is None:
+            out = torch.empty((int(n_clips), int(n_samples)), dtype=torch.float32, device=self.device)
+        elif out.ndim != 2 or out.shape[0] < n_clips or out.shape[1] < n_samples or out.stride(1) != 1 or out.device != self.device:
+            raise ValueError("out must be a (>= n_clips, >= n_samples) float32 row-major tensor on the plan's device")
+        done = 0
+        with torch.cuda.device(self.device):
+            while done < n_clips:  # the launch grid holds 65 535 clips
+                n = min(32768, n_clips - done)
+                _lib.check(self.lib.ast_synth_clips(_ptr(out[done:]), out.stride(0), n, int(n_samples),
+                                                    int(first_clip_id) + done, int(violin_from_id), _stream_ptr(self.device)))
+                done += n
+        return out[:n_clips, :n_samples]
+
     # ------------------------------------------------------------------ a1: get_STFT, batched
     def stft(self, wave: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``(B, L)`` -> ``(B, 2, T, 513)``, ``T = 1 + L // 256`` (``utilityFunctions.py:12-37``)."""

@@ -12,7 +12,10 @@ bracketed by barrier + synchronize, max over ranks.  Rank 0 prints ONE JSON line
 Extra objects on the line: ``roofline`` (dominant kernel, timed live with CUDA events in a second pass
 of the same K steps), ``cpu_baseline`` (oracle port of the reference CPU path on the host cores, rank 0,
 N = 1), ``e2e`` (same metric through the public API from pinned HOST buffers, H2D + D2H inside the timed
-region), ``istft`` (the reconstruction leg of the metric), ``clocks`` (nvidia-smi during the timed region).
+region, with the platform's plain-copy ceiling beside it), ``istft`` (the reconstruction leg of the metric),
+``ragged`` (configs[2]: variable-length padded batch), ``stats`` (configs[3]: 100 000 synthetic clips sharded over
+the ranks, one NCCL all-reduce of the partial moments, determinism check against a 1-rank pass), ``istft_sweep``
+(configs[4]: B = 1 ... 4096 per rank), ``clocks`` (nvidia-smi during the timed region).
 """
 from __future__ import annotations
 
@@ -140,9 +143,81 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+def host_info():
+    """CPU model, core count and the library versions the CPU arm runs on."""
+    import numpy as np
+    import scipy
+    import torch
+
+    model = None
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    mkl = None
+    for line in torch.__config__.show().splitlines():
+        if "Math Kernel Library" in line or "MKL" in line and "Version" in line:
+            mkl = line.strip(" -")
+            break
+    return {"cpu_model": model, "os_cpu_count": os.cpu_count(), "torch": torch.__version__, "numpy": np.__version__,
+            "scipy": scipy.__version__, "mkl": mkl, "torch_fft_backend": "mkl" if torch.backends.mkl.is_available() else "pocketfft"}
+
+
+def _median(xs):
+    xs = sorted(xs)
+    n = len(xs)
+    return xs[n // 2] if n % 2 else 0.5 * (xs[n // 2 - 1] + xs[n // 2])
+
+
+def time_cpu_path(wave, mean, std, threads, reps, warmup=1):
+    """Median seconds per repetition of the reference CPU path over ``wave`` with ``threads`` intra-op threads."""
+    import torch
+
+    from oracle import cpu_baseline as cb
+
+    prev = torch.get_num_threads()
+    torch.set_num_threads(threads)
+    try:
+        for _ in range(warmup):
+            cb.features_batch(wave, mean, std)
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            out = cb.features_batch(wave, mean, std)
+            times.append(time.perf_counter() - t0)
+        assert tuple(out.shape) == (wave.shape[0], 4, 2, 287, 597)
+    finally:
+        torch.set_num_threads(prev)
+    return _median(times), times
+
+
+def time_cpu_istft(spec, threads, reps, warmup=1):
+    import torch
+
+    from oracle import cpu_baseline as cb
+
+    prev = torch.get_num_threads()
+    torch.set_num_threads(threads)
+    try:
+        for _ in range(warmup):
+            cb.istft_batch(spec[:1])
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            cb.istft_batch(spec)
+            times.append(time.perf_counter() - t0)
+    finally:
+        torch.set_num_threads(prev)
+    return _median(times), times
+
+
 def run_reference(args, rank, world):
     """The reference's CPU path (oracle port: torch.stft + restated librosa CQT + eager normalise / section
-    loops) on the host cores, bounded sample per step."""
+    loops) on the host cores, bounded sample per step.  Under torchrun only rank 0 runs it."""
     if rank != 0:
         return
     import numpy as np
@@ -151,59 +226,159 @@ def run_reference(args, rank, world):
     from oracle import cpu_baseline as cb
 
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     sample_clips = 4
     wave = torch.from_numpy(make_clips(4)[:sample_clips].copy())
     z = np.load(STATS_NPZ)
     mean = torch.from_numpy(np.concatenate([z["stft_mean"], z["cqt_mean"]], axis=1))
     std = torch.from_numpy(np.concatenate([z["stft_std"], z["cqt_std"]], axis=1))
+    # the line's value: all host threads, K timed steps after W warm-ups (the contract's timing)
+    torch.set_num_threads(cores)
     for _ in range(args.warmup):
         cb.features_batch(wave, mean, std)
-    t0 = time.perf_counter()
+    step_s = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         out = cb.features_batch(wave, mean, std)
-    dt = time.perf_counter() - t0
+        step_s.append(time.perf_counter() - t0)
+    dt = sum(step_s)
     assert tuple(out.shape) == (sample_clips, 4, 2, 287, 597)
     value = sample_clips * CLIP_SECONDS * args.steps / dt
+    # beside it: the same sample on ONE thread (torch's CPU stft is slower with many threads than with one)
+    one_s, _ = time_cpu_path(wave, mean, std, 1, reps=max(5, min(args.steps, 7)))
     sample = f"{sample_clips} of the 64 clips per step (per-clip loop, as the reference DataLoader with num_workers=0)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "reference_ranks": 1,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "median_value": sample_clips * CLIP_SECONDS / _median(step_s), "repetitions": args.steps,
+                         "one_thread": {"value": sample_clips * CLIP_SECONDS / one_s, "cores": 1,
+                                        "repetitions": max(5, min(args.steps, 7)), "statistic": "median"},
+                         "host": host_info()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "torch.stft / eager torch ops exactly as utilityFunctions.py + dataloader.py call them; the CQT is the "
-                "NumPy/SciPy restatement of librosa.cqt (librosa is not installable here)",
+                "NumPy/SciPy restatement of librosa.cqt (librosa is not installable here).  ONE CPU process on rank 0 "
+                "at every --gpus N: a per-N ratio compares N GPUs with one host process.",
     }
     print(json.dumps(line), flush=True)
 
 
 def cpu_baseline_leg(wave_np, mean, std):
+    """the reference CPU path on all host threads AND on one thread, >= 5 repetitions after a warm-up,
+    median; CPU model and library versions beside the numbers.  Bounded sample (4 clips per repetition)."""
     import torch
 
-    from oracle import cpu_baseline as cb
-
     cores = os.cpu_count() or 1
-    prev = torch.get_num_threads()
-    torch.set_num_threads(cores)
-    n = 32
+    n, reps = 4, 5
     wave = torch.from_numpy(wave_np[:n].copy())
-    cb.features_batch(wave[:1], mean, std)  # warm-up (FFT plans, filter tables)
-    t0 = time.perf_counter()
-    cb.features_batch(wave, mean, std)
-    dt = time.perf_counter() - t0
-    spec = torch.randn(8, 4, 2, 287, 513)
-    cb.istft_batch(spec[:1])
-    t1 = time.perf_counter()
-    cb.istft_batch(spec)
-    dt_i = time.perf_counter() - t1
-    torch.set_num_threads(prev)
+    all_s, all_times = time_cpu_path(wave, mean, std, cores, reps)
+    one_s, one_times = time_cpu_path(wave, mean, std, 1, reps)
+    spec = torch.randn(4, 4, 2, 287, 513)
+    i_all, _ = time_cpu_istft(spec, cores, reps)
+    i_one, _ = time_cpu_istft(spec, 1, reps)
     return {
-        "value": n * CLIP_SECONDS / dt, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": f"{n} of the 64 clips, one pass, per-clip loop (torch.stft + restated librosa CQT + eager normalise/sections)",
-        "istft_value": 8 * ISTFT_SECONDS / dt_i, "istft_sample": "8 clips merge + torch.istft",
+        "value": n * CLIP_SECONDS / all_s, "unit": UNIT, "cores": cores, "kind": "port", "statistic": "median", "repetitions": reps,
+        "sample": f"{n} of the 64 clips per repetition, per-clip loop (torch.stft + restated librosa CQT + eager normalise/sections)",
+        "spread": {"min_s": min(all_times), "max_s": max(all_times)},
+        "one_thread": {"value": n * CLIP_SECONDS / one_s, "cores": 1, "statistic": "median", "repetitions": reps,
+                       "spread": {"min_s": min(one_times), "max_s": max(one_times)}},
+        "istft_value": 4 * ISTFT_SECONDS / i_all, "istft_one_thread_value": 4 * ISTFT_SECONDS / i_one,
+        "istft_sample": "4 clips merge + torch.istft per repetition, median of 5",
+        "host": host_info(),
+        "note": "the CQT part is the repository's restatement of librosa.cqt, not librosa itself (not installable here)",
     }
+
+
+STATS_TOTAL_CLIPS = int(os.environ.get("AST_BENCH_STATS_CLIPS", "100000"))
+STATS_RESIDENT_CLIPS = 12500   # 11 GB of waveforms resident per pass
+STATS_BATCH = 250
+
+
+def stats_pass(fe, stats_mod, clip_ids, total, resident, batch_clips):
+    """Per-bin moments of the synthetic clips ``clip_ids`` (a range) on this GPU.  Clips are generated on the device
+    in resident blocks OUTSIDE the timed spans (inputs resident in HBM when a span starts); returns (acc, counts, ms)."""
+    import torch
+
+    acc, counts = fe.new_stats_accumulator(2)
+    half = total // 2
+    ms = 0.0
+    buf = None
+    start, stop = clip_ids.start, clip_ids.stop
+    while start < stop:
+        n = min(resident, stop - start)
+        if buf is None:
+            buf = torch.empty((min(resident, stop - clip_ids.start), CLIP_SAMPLES), dtype=torch.float32, device=fe.device)
+        fe.synth_clips(n, first_clip_id=start, violin_from_id=half, n_samples=CLIP_SAMPLES, out=buf)
+        gid = (torch.arange(start, start + n, device=fe.device) >= half).to(torch.int32)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(0, n, batch_clips):
+            m = min(batch_clips, n - k)
+            fe.stats_accumulate(buf[k:k + m], acc, counts, group_ids=gid[k:k + m])
+        e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+        start += n
+    del buf
+    return acc, counts, ms
+
+
+def stats_leg(fe, device, rank, world, dist, barrier):
+    """configs[3]: unified + per-instrument per-bin mean / std over STATS_TOTAL_CLIPS synthetic clips (first half
+    piano-like, second half violin-like), contiguous shards over the ranks, ONE all-reduce(sum) of the float64 partial
+    moments (compute_separated_stats.py:16-43, compute_unified_stats.py:25-50)."""
+    import zlib
+
+    import numpy as np
+    import torch
+
+    stats_mod = importlib.import_module("audio_style_transfer_b200.stats")
+    total = STATS_TOTAL_CLIPS
+    shard = stats_mod.shard_range(total, rank, world)
+    stats_pass(fe, stats_mod, range(0, min(500, total)), total, STATS_RESIDENT_CLIPS, STATS_BATCH)   # warm-up
+    barrier()
+    acc, counts, ms_compute = stats_pass(fe, stats_mod, shard, total, STATS_RESIDENT_CLIPS, STATS_BATCH)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    stats_mod.allreduce_accumulators(acc, counts)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_allreduce = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_compute, ms_allreduce], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_compute, ms_allreduce = float(t[0]), float(t[1])
+    res = stats_mod.finalize_all(acc, counts)
+    crc = {k: zlib.crc32(np.concatenate([m.ravel(), s_.ravel()]).tobytes()) for k, (m, s_) in sorted(res.items())}
+    determinism = None
+    if world > 1:
+        # the same dataset on ONE rank: the float64 sums differ only by the order of the rank partials
+        if rank == 0:
+            acc1, counts1, _ = stats_pass(fe, stats_mod, range(0, total), total, STATS_RESIDENT_CLIPS, STATS_BATCH)
+            a, b = acc.cpu().numpy(), acc1.cpu().numpy()
+            nz = np.abs(b) > 0
+            rel = float((np.abs(a - b)[nz] / np.abs(b)[nz]).max()) if nz.any() else 0.0
+            res1 = stats_mod.finalize_all(acc1, counts1)
+            same32 = all(np.array_equal(res[k][0], res1[k][0]) and np.array_equal(res[k][1], res1[k][1]) for k in res)
+            determinism = {"max_rel_diff_f64_sums": rel, "rtol": 1e-12, "ok": bool(rel <= 1e-12),
+                           "counts_equal": bool(np.array_equal(counts.cpu().numpy(), counts1.cpu().numpy())),
+                           "float32_mean_std_bit_identical": bool(same32),
+                           "how": f"rank 0 repeated all {total} clips alone and compared with the {world}-rank all-reduced sums"}
+        barrier()
+    total_ms = ms_compute + ms_allreduce
+    return {"metric": "audio-sec/sec dataset statistics (STFT+CQT -> per-clip per-bin mean / unbiased var -> sums)", "unit": UNIT,
+            "value": total * CLIP_SECONDS / (total_ms / 1e3), "clips_total": total, "clips_per_rank": len(shard),
+            "ms_compute_max_over_ranks": ms_compute, "allreduce_us": 1e3 * ms_allreduce, "ms_total": total_ms,
+            "allreduce_bytes": int((acc.numel() + counts.numel()) * 8), "backend": "nccl" if world > 1 else "none (1 rank)",
+            "counts": [float(c) for c in counts.cpu()], "groups": sorted(res),
+            "result_crc32": crc, "determinism": determinism, "scaling": "strong (fixed 100 000-clip dataset over N ranks)",
+            "workload": f"configs[3]: {total} synthetic 10 s clips (ast_synth_clips, clip id -> seed 1000 + id; first half piano-like, "
+                        f"second half violin-like), {len(shard)} per rank in resident blocks of {STATS_RESIDENT_CLIPS} "
+                        f"generated outside the timed spans, {STATS_BATCH}-clip calls of ast_stats_accumulate"}
 
 
 def main():
@@ -296,6 +471,63 @@ def main():
     ms_load = timed(load_step, args.steps, args.warmup) / args.steps
     del stereo
 
+    # ---- configs[2]: variable-length padded batch (lengths U{44100 .. 220500}, seed 7), sections + n_sections
+    g7 = torch.Generator().manual_seed(7)
+    rag_len = torch.randint(44100, CLIP_SAMPLES + 1, (CLIPS_PER_GPU,), generator=g7, dtype=torch.int64).to(torch.int32)
+    rag_wave = wave.clone()
+    rag_wave[torch.arange(CLIP_SAMPLES, device=device)[None, :] >= rag_len.to(device)[:, None]] = 0.0
+    rag_len_d = rag_len.to(device)
+
+    def ragged_step():
+        fe.features(rag_wave, lengths=rag_len_d, mean=mean_d, std=std_d, layout="sections", out=out)
+
+    ms_rag = timed(ragged_step, args.steps, args.warmup) / args.steps
+    rag_audio_s = float(rag_len.sum()) / SAMPLE_RATE
+    _, rag_counts = fe.features(rag_wave, lengths=rag_len_d, mean=mean_d, std=std_d, layout="sections", out=out)
+    ragged = {"metric": "audio-sec/sec STFT+CQT+norm, variable-length padded batch", "unit": UNIT,
+              "value": world * rag_audio_s / (ms_rag / 1e3), "ms_per_step": ms_rag, "gpu_launches": 4 * args.steps,
+              "workload": "configs[2]: 64 clips per GPU, lengths ~ U{44100..220500} (torch.Generator().manual_seed(7)), zero-padded "
+                          "to 220500, lengths[B] int32 -> (64,4,2,287,597) + n_sections[B]; sections past a clip's end are zeros",
+              "valid_audio_s_per_gpu": rag_audio_s, "padded_audio_s_per_gpu": CLIPS_PER_GPU * CLIP_SECONDS,
+              "padded_value": world * CLIPS_PER_GPU * CLIP_SECONDS / (ms_rag / 1e3),
+              "n_sections_histogram": {str(k): int((rag_counts == k).sum()) for k in range(5)}}
+    del rag_wave
+
+    # ---- configs[4]: decoder-output iSTFT sweep, B = 1 ... 4096 per rank, L2 flushed before every timed call
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    sweep = []
+    for B in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096):
+        spec_b = torch.randn((B, 4, 2, 287, 513), dtype=torch.float32, device=device)
+        reps = 10 if B <= 512 else 3
+        for _ in range(3):
+            fe.istft(spec_b, layout="sections", overlap=96, original_size=862)
+        barrier()
+        ms = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fe.istft(spec_b, layout="sections", overlap=96, original_size=862)
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+        ms /= reps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        sweep.append({"B": B, "ms": ms, "value": world * B * ISTFT_SECONDS / (ms / 1e3),
+                      "gbs_per_gpu": B * BYTES_ISTFT_PATH / (ms * 1e-3) / 1e9})
+        del spec_b
+    del flush
+    istft_sweep = {"metric": "audio-sec/sec iSTFT (merge + inverse STFT)", "unit": UNIT,
+                   "workload": "configs[4]: decoder-shaped randn (B,4,2,287,513) per GPU -> merge(overlap 96) -> iSTFT -> (B,219904); "
+                               "L2 flushed (256 MB write) before every timed call, CUDA events, max over ranks",
+                   "points": sweep, "best_value": max(p_["value"] for p_ in sweep)}
+
+    # ---- configs[3]: dataset statistics over 100 000 synthetic clips sharded over the ranks + ONE NCCL all-reduce
+    stats_obj = stats_leg(fe, device, rank, world, dist if world > 1 else None, barrier)
+
     # ---- roofline pass: the same K steps with per-kernel CUDA events (ast_profile_*), rank-local
     lib.profile_enable(True)
     for _ in range(args.steps):
@@ -331,13 +563,20 @@ def main():
     if dom:
         a = kernels[dom]["achieved_gbs"]
         # DRAM bytes per launch of each kernel at this workload, from the committed ncu --set full capture
-        traffic = None
+        traffic, traffic_src = None, None
         traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_path):
-            traffic = json.load(open(traffic_path)).get("dram_bytes_per_launch", {}).get(dom)
+            tj = json.load(open(traffic_path))
+            traffic = tj.get("dram_bytes_per_launch", {}).get(dom)
+            # NOT measured by this run: an ncu --set full capture of an earlier commit, named here
+            traffic_src = {"file": "profiles/traffic.json", "captured_at_commit": tj.get("commit"),
+                           "ncu_report": tj.get("source"), "this_run": False}
         roofline = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
-                    "traffic": traffic, "peak_source": peak_src,
-                    "share_of_step": kernels[dom]["ms_per_step"] / feature_ms if feature_ms else None,
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                    # per-kernel times come from a second pass with events between the launches (no programmatic
+                    # overlap): a share of the SERIALISED sum, not of ms_per_step
+                    "share_of_serialised_sum": kernels[dom]["ms_per_step"] / feature_ms if feature_ms else None,
+                    "serialised_sum_ms": feature_ms,
                     "path": {"bytes_per_clip": BYTES_FEATURE_PATH,
                              "achieved": BYTES_FEATURE_PATH * CLIPS_PER_GPU / (ms_step * 1e-3) / 1e9,
                              "frac": BYTES_FEATURE_PATH * CLIPS_PER_GPU / (ms_step * 1e-3) / 1e9 / peak},
@@ -368,11 +607,44 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t[0])
-        e2e = {"value": world * CLIPS_PER_GPU * CLIP_SECONDS * e2e_steps / dt, "unit": UNIT,
+        e2e_value = world * CLIPS_PER_GPU * CLIP_SECONDS * e2e_steps / dt
+        # the platform's ceiling for this step: the same 56 MB H2D and 351 MB D2H as plain pinned copies on two streams
+        # (full duplex), no kernels, all ranks at once
+        s_in, s_out = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+        dev_in = torch.empty_like(wave)
+
+        def copy_step():
+            with torch.cuda.stream(s_in):
+                dev_in.copy_(host_in, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                host_out.copy_(out, non_blocking=True)
+            s_in.synchronize()
+            s_out.synchronize()
+
+        copy_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            copy_step()
+        dt_c = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt_c], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_c = float(t[0])
+        ceiling = world * CLIPS_PER_GPU * CLIP_SECONDS * e2e_steps / dt_c
+        e2e = {"value": e2e_value, "unit": UNIT,
                "h2d_bytes_per_step": int(host_in.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4),
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps, "numa": numa,
+               "pcie_ceiling": {"value": ceiling, "unit": UNIT, "ms_per_step": 1e3 * dt_c / e2e_steps,
+                                "h2d_gbs_per_gpu": host_in.numel() * 4 / (dt_c / e2e_steps) / 1e9,
+                                "d2h_gbs_per_gpu": host_out.numel() * 4 / (dt_c / e2e_steps) / 1e9,
+                                "how": "plain pinned cudaMemcpyAsync H2D 56 MB || D2H 351 MB on two streams, no kernels, "
+                                       "all ranks concurrently, max over ranks"},
+               "frac_of_ceiling": e2e_value / ceiling,
                "how": "FrontEnd.features_host: pinned host waveforms -> H2D -> ast_features_forward -> D2H of the full 351 MB "
-                      "feature tensor into pinned host memory, 16-clip chunks pipelined over 3 streams, synchronize every step"}
+                      "feature tensor into pinned host memory; 16-clip chunks, kernels on ONE stream, copies on two side "
+                      "streams ordered by events over 3 rotating buffers, synchronize every step"}
+        del dev_in
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -388,6 +660,7 @@ def main():
             "istft": {"metric": "audio-sec/sec iSTFT (merge + inverse STFT)", "value": istft_value, "unit": UNIT,
                       "ms_per_step": ms_istft, "gpu_launches": args.steps,
                       "workload": "configs[4] at B=64 per GPU: (64,4,2,287,513) -> (64,219904)"},
+            "ragged": ragged, "stats": stats_obj, "istft_sweep": istft_sweep,
             "load_audio": {"metric": "audio-sec/sec load_audio device part (pad/cut + 44.1k->22.05k resample + stereo mean)",
                            "value": world * CLIPS_PER_GPU * CLIP_SECONDS / (ms_load / 1e3), "unit": UNIT,
                            "ms_per_step": ms_load, "bytes_per_clip": BYTES_LOAD_AUDIO,

@@ -246,6 +246,16 @@ size_t ast_instrumentation_similarity_workspace_bytes(const ast_plan* plan, int6
 int ast_instrumentation_similarity(const ast_plan* plan, const float* a, int64_t n_a, const float* b, int64_t n_b,
                                    void* workspace, size_t workspace_bytes, double* result, void* stream);
 
+/* ---- synthetic workload (no counterpart in the reference) ---------------------------------- */
+/*
+ * Dataset-scale inputs for BASELINE.json configs[3] (100 000 clips): clip `first_clip_id + b` is written
+ * to out + b * out_stride.  Every sample is a pure function of (clip id, sample index): piano-like decaying notes for
+ * ids < violin_from_id, violin-like sustained notes with vibrato from there on, plus white noise, RMS about 0.07.
+ * Counter-based (integer hash of 1000 + clip id), so any rank regenerates any clip bit for bit in any chunking.
+ */
+int ast_synth_clips(float* out, int64_t out_stride, int32_t n_clips, int64_t n_samples, int64_t first_clip_id,
+                    int64_t violin_from_id, void* stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /*
  * Per-kernel device timing (no counterpart in the reference).  While enabled, every kernel launch
