@@ -42,13 +42,17 @@ void set_overlap_streams(int on) { g_overlap_streams = on; }
 static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 struct Workspace {
-  float2* stats_table;  // batch * 2 * 597 (mean, rstd)
+  float2* stats_table;  // batch * 2 * 597 (mean, rstd): the CQT epilogue's table
+  float4* stat4;        // batch * kStat4Stride: the STFT kernel's per-bin (mean_re, rstd_re, mean_im, rstd_im)
   float* octaves;       // batch * cqt_ws_clip_stride floats
   int* dec_flags;       // the decimator's per-tile completion counters
   size_t used;
 };
 
-static size_t stats_table_bytes(int batch) { return align_up(sizeof(float2) * 2 * kFTotal * (size_t)(batch > 0 ? batch : 1)); }
+static size_t stats_table_bytes(int batch) {
+  const size_t rows = (size_t)(batch > 0 ? batch : 1);
+  return align_up(sizeof(float2) * 2 * kFTotal * rows) + align_up(sizeof(float4) * kStat4Stride * rows);
+}
 static size_t octave_bytes(int batch, long long max_samples) {
   return align_up(sizeof(float) * (size_t)cqt_ws_clip_stride(max_samples) * (size_t)batch);
 }
@@ -64,10 +68,38 @@ static int carve(void* ws, size_t ws_bytes, int batch, long long max_samples, Wo
   if (reinterpret_cast<uintptr_t>(ws) & 255) return fail(AST_ERR_INVALID_ARG, "workspace must be 256-byte aligned");
   char* p = static_cast<char*>(ws);
   w->stats_table = reinterpret_cast<float2*>(p);
+  w->stat4 = reinterpret_cast<float4*>(p + align_up(sizeof(float2) * 2 * kFTotal * (size_t)(batch > 0 ? batch : 1)));
   w->octaves = reinterpret_cast<float*>(p + stats_table_bytes(batch));
   w->dec_flags = reinterpret_cast<int*>(p + stats_table_bytes(batch) + octave_bytes(batch, max_samples));
   w->used = need;
   return AST_OK;
+}
+
+// ---- statistics pass: per-tile partial moments instead of features (stft.cu / cqt_tc.cu statistics mode) ------------
+struct StatsScratch {
+  float2* part_stft;   // batch * stft_tiles_max * 2 * 513
+  float* part_n;       // batch * stft_tiles_max
+  float2* part_cqt;    // batch * 7 * cqt_tiles * 4 * 24
+  double* clip_stats;  // batch * 4 * 597
+};
+static int stats_stft_tiles_max(long long max_samples) {
+  // the STFT kernel's statistics mode works in fixed tiles of 64 frame pairs = 128 frames (stft.cu)
+  return (int)((num_frames(max_samples) + 127) / 128);
+}
+static int stats_cqt_tiles(long long max_samples) { return (num_frames(max_samples) + 127) / 128; }
+static size_t stats_scratch_bytes(int batch, long long max_samples, StatsScratch* s, char* base) {
+  const size_t b = (size_t)(batch > 0 ? batch : 1);
+  const size_t n0 = align_up(sizeof(float2) * b * stats_stft_tiles_max(max_samples) * 2 * kFStft);
+  const size_t n1 = align_up(sizeof(float) * b * stats_stft_tiles_max(max_samples));
+  const size_t n2 = align_up(sizeof(float2) * b * kOctaves * stats_cqt_tiles(max_samples) * 4 * kCqtCols);
+  const size_t n3 = align_up(sizeof(double) * 4 * kFTotal * b);
+  if (s) {
+    s->part_stft = reinterpret_cast<float2*>(base);
+    s->part_n = reinterpret_cast<float*>(base + n0);
+    s->part_cqt = reinterpret_cast<float2*>(base + n0 + n1);
+    s->clip_stats = reinterpret_cast<double*>(base + n0 + n1 + n2);
+  }
+  return n0 + n1 + n2 + n3;
 }
 
 static int check_wave(const ast_plan* plan, const float* wave, int batch, long long max_samples, long long wave_stride) {
@@ -96,6 +128,7 @@ static OutSpec make_out(const ast_plan* plan, float* out, int layout, int dim1, 
   o.stats_clip_stride = 0;
   o.f_stats = kFTotal;
   o.stats_off = 0;
+  o.cqt_part = nullptr;
   return o;
 }
 }  // namespace ast
@@ -112,9 +145,9 @@ size_t ast_workspace_bytes(const ast_plan* plan, int32_t batch, int64_t max_samp
 
 size_t ast_stats_workspace_bytes(const ast_plan* plan, int32_t batch, int64_t max_samples) {
   if (batch < 0 || max_samples < 0) return 0;
-  const size_t t = (size_t)num_frames(max_samples);
-  return ast_workspace_bytes(plan, batch, max_samples) + align_up(sizeof(float) * 2 * t * kFTotal * (size_t)batch) +
-         align_up(sizeof(double) * 4 * kFTotal * (size_t)batch);
+  // the feature call's scratch + per-tile partial moments + per-clip moments; the features themselves are never stored.
+  // ast_stats_accumulate_features needs only the per-clip moments (the last term) and accepts this figure.
+  return ast_workspace_bytes(plan, batch, max_samples) + stats_scratch_bytes(batch, max_samples, nullptr, nullptr);
 }
 
 int ast_stft_forward(const ast_plan* plan, const float* wave, const int32_t* lengths, int32_t batch, int64_t max_samples,
@@ -165,13 +198,13 @@ int ast_features_forward(const ast_plan* plan, const float* wave, const int32_t*
   // completion counters, and the decimator is launched as its programmatic dependent
   const bool chained = g_overlap_streams && !profile_on() && use_tc_decimator() && use_tc_cqt() && batch > 0;
   if (chained) {
-    rc = launch_features_prologue(mean, std_, eps, n_stats, w.stats_table, lengths, batch, max_samples, layout, dim1,
+    rc = launch_features_prologue(mean, std_, eps, n_stats, w.stats_table, w.stat4, lengths, batch, max_samples, layout, dim1,
                                   plan->cfg.window_size, plan->cfg.overlap_frames, n_sections, w.dec_flags,
                                   tail_counter_index(batch, max_samples) + 1, st);
     if (rc != AST_OK) return rc;
   } else {
     if (mean) {
-      rc = launch_prep_stats(mean, std_, eps, n_stats, w.stats_table, st);
+      rc = launch_prep_stats(mean, std_, eps, n_stats, w.stats_table, w.stat4, st);
       if (rc != AST_OK) return rc;
     }
     if (n_sections) {
@@ -188,8 +221,10 @@ int ast_features_forward(const ast_plan* plan, const float* wave, const int32_t*
   oq.f_off = kFStft;
   oq.stats_off = kFStft;
   const long long ws_stride = cqt_ws_clip_stride(max_samples);
+  const float4* stat4 = mean ? w.stat4 : nullptr;
+  const int stat4_stride = stats_per_clip ? kStat4Stride : 0;
   if (!g_overlap_streams || profile_on()) {
-    rc = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st);
+    rc = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st, 0, false, nullptr, stat4, stat4_stride);
     if (rc != AST_OK) return rc;
     rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, st);
     if (rc != AST_OK) return rc;
@@ -209,7 +244,8 @@ int ast_features_forward(const ast_plan* plan, const float* wave, const int32_t*
   // CTA to finish then waits for that grid (tail counter), so that "the call's last kernel is complete" means the whole
   // call is complete - which a following programmatic dependent (the next call's prologue, the iSTFT) relies on
   return launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st, 0, /*pdl=*/chained,
-                     chained ? reinterpret_cast<unsigned int*>(w.dec_flags + tail_counter_index(batch, max_samples)) : nullptr);
+                     chained ? reinterpret_cast<unsigned int*>(w.dec_flags + tail_counter_index(batch, max_samples)) : nullptr,
+                     stat4, stat4_stride);
 }
 
 int ast_istft_forward(const ast_plan* plan, const float* spec, int32_t batch, int32_t dim1, int32_t f_in, int32_t layout,
@@ -257,27 +293,38 @@ int ast_stats_accumulate(const ast_plan* plan, const float* wave, const int32_t*
   if (!acc || !counts || n_groups <= 0) return fail(AST_ERR_INVALID_ARG, "ast_stats_accumulate: bad argument");
   const size_t need = ast_stats_workspace_bytes(plan, batch, max_samples);
   if (!workspace || workspace_bytes < need) return fail(AST_ERR_WORKSPACE, "workspace too small: need %zu bytes", need);
-  const int t_dim = num_frames(max_samples);
+  if (batch == 0) return AST_OK;
   const size_t base = ast_workspace_bytes(plan, batch, max_samples);
-  char* p = static_cast<char*>(workspace);
-  float* feats = reinterpret_cast<float*>(p + base);
-  double* clip_stats = reinterpret_cast<double*>(p + base + align_up(sizeof(float) * 2 * (size_t)t_dim * kFTotal * (size_t)batch));
-  int32_t* n_frames = nullptr;
-  // raw (un-normalised) flat features, exactly what compute_stats reduces (compute_separated_stats.py:22-28)
-  rc = ast_features_forward(plan, wave, lengths, batch, max_samples, wave_stride, nullptr, nullptr, 0, 0.f, workspace, base,
-                            feats, t_dim, AST_LAYOUT_FLAT, nullptr, stream);
+  Workspace w;
+  rc = carve(workspace, base, batch, max_samples, &w);
   if (rc != AST_OK) return rc;
+  StatsScratch sc;
+  stats_scratch_bytes(batch, max_samples, &sc, static_cast<char*>(workspace) + base);
   cudaStream_t st = (cudaStream_t)stream;
-  if (lengths) {
-    // frame counts per clip, kept in the (now free) normalisation-table region of the workspace
-    n_frames = reinterpret_cast<int32_t*>(p);
-    rc = launch_count_sections(lengths, batch, max_samples, AST_LAYOUT_FLAT, t_dim, plan->cfg.window_size,
-                               plan->cfg.overlap_frames, n_frames, st);
-    if (rc != AST_OK) return rc;
-  }
-  rc = launch_clip_stats(feats, n_frames, batch, t_dim, kFTotal, clip_stats, st);
+  // The raw (un-normalised) features of compute_stats (compute_separated_stats.py:22-28) are never stored: the STFT and
+  // the CQT projection run in statistics mode and leave per-tile (mean, M2) partials (~ 100 KB per clip against the
+  // 4.1 MB of a flat feature tensor), which one small kernel merges per clip in frame order.
+  const int t_dim = num_frames(max_samples);
+  OutSpec o = make_out(plan, nullptr, AST_LAYOUT_FLAT, t_dim, kFTotal, 0);
+  const int stft_tiles = stft_tiles_per_clip(plan, batch, t_dim, /*stats_mode=*/true);
+  if (stft_tiles > stats_stft_tiles_max(max_samples)) return fail(AST_ERR_WORKSPACE, "internal: statistics tile bound exceeded");
+  rc = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st, 0, false, nullptr, nullptr, 0, sc.part_stft,
+                   sc.part_n);
   if (rc != AST_OK) return rc;
-  return launch_stats_accumulate(clip_stats, group_ids, batch, kFTotal, n_groups, acc, counts, st);
+  const long long ws_stride = cqt_ws_clip_stride(max_samples);
+  rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, st);
+  if (rc != AST_OK) return rc;
+  OutSpec oq = o;
+  oq.f_off = kFStft;
+  oq.stats_off = kFStft;
+  oq.cqt_part = sc.part_cqt;
+  rc = launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride,
+                  use_tc_decimator() ? w.dec_flags : nullptr, oq, st);
+  if (rc != AST_OK) return rc;
+  rc = launch_stats_finalize_clips(sc.part_stft, sc.part_n, stft_tiles, sc.part_cqt, stats_cqt_tiles(max_samples), lengths,
+                                   max_samples, batch, sc.clip_stats, st);
+  if (rc != AST_OK) return rc;
+  return launch_stats_accumulate(sc.clip_stats, group_ids, batch, kFTotal, n_groups, acc, counts, st);
 }
 
 int ast_profile_enable(int32_t on) {

@@ -97,6 +97,8 @@ struct OutSpec {
   int stats_clip_stride;  // 0 (shared) or 2 * f_stats
   int f_stats;            // columns per stats row
   int stats_off;          // column in the stats row of this kernel's first bin
+  float2* cqt_part;       // statistics mode of the CQT projection: [clip][octave][tile][quadrant][24] (mean, M2) of the
+                          // quadrant's (<= 32) live frames; nothing else is stored when set
 };
 
 __host__ __device__ inline int num_frames(long long n_samples) { return 1 + (int)(n_samples / kHop); }
@@ -157,6 +159,7 @@ struct ast_plan {
   int sm_count;
   float2* d_tw1;        // stage-1 twiddles [16][16]  (fft_core.h)
   float2* d_tw2;        // stage-2 twiddles [16][64]
+  float2* d_tw32;       // [32][32] W_1024^(n2 k1): the one-warp 32 x 32 transform (stft.cu)
   float* d_hann;        // 1024 periodic Hann
   float* d_hann_inv_n;  // Hann / 1024 (iSTFT synthesis window with the irfft scale folded in)
   float* d_hann_sq;     // Hann^2 (iSTFT envelope)
@@ -169,15 +172,24 @@ struct ast_plan {
 
 namespace ast {
 // kernels' host launchers (each returns an ast_status)
-int launch_prep_stats(const float* mean, const float* std, float eps, int n, float2* table, cudaStream_t st);
+constexpr int kStat4Stride = 516;   // float4 per clip of the STFT kernel's per-bin statistics (513 bins, padded)
+int launch_prep_stats(const float* mean, const float* std, float eps, int n, float2* table, float4* stat4, cudaStream_t st);
 int launch_count_sections(const int32_t* lengths, int batch, long long max_samples, int layout, int dim1,
                           int window, int overlap, int32_t* n_out, cudaStream_t st);
+// stat4: per-bin (-mean_re, -mean_im, rstd_re, rstd_im) of the 513 STFT bins, kStat4Stride float4 per clip (or one shared
+// row), or nullptr; part / part_n: statistics mode (per-tile moments instead of any output), see stft.cu
 int launch_stft(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
                 long long wave_stride, const OutSpec& out, cudaStream_t st, int pad_zero = 0, bool pdl = false,
-                unsigned int* tail_counter = nullptr);
-int launch_features_prologue(const float* mean, const float* std_, float eps, int n_stats, float2* table, const int32_t* lengths,
-                             int batch, long long max_samples, int layout, int dim1, int window, int overlap, int32_t* n_out,
-                             int* flags, int n_flags, cudaStream_t st);
+                unsigned int* tail_counter = nullptr, const float4* stat4 = nullptr, int stat4_clip_stride = 0,
+                float2* part = nullptr, float* part_n = nullptr);
+int stft_tiles_per_clip(const ast_plan* plan, int batch, int slots, bool stats_mode);   // grid.x of the launch above
+int launch_features_prologue(const float* mean, const float* std_, float eps, int n_stats, float2* table, float4* stat4,
+                             const int32_t* lengths, int batch, long long max_samples, int layout, int dim1, int window,
+                             int overlap, int32_t* n_out, int* flags, int n_flags, cudaStream_t st);
+// K6 fused: per-clip moments from the per-tile partials the STFT / CQT kernels leave in statistics mode
+int launch_stats_finalize_clips(const float2* part_stft, const float* part_n, int stft_tiles, const float2* part_cqt,
+                                int cqt_tiles, const int32_t* lengths, long long max_samples, int batch, double* clip_stats,
+                                cudaStream_t st);
 int launch_decimate_cascade(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch,
                             long long max_samples, long long wave_stride, float* ws, long long ws_clip_stride,
                             int* flags, cudaStream_t st, bool flags_zeroed = false);

@@ -448,7 +448,10 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
       float sc, mean, rstd;   // lane c < 24: constants of output column c (12 re then 12 im)
       int off0, off1;         // this lane's frame: destination rows as offsets from clip_out (column col0 included)
       int flags;              // bit 0 / 1: row 0 / 1 live (data, else zeros); bit 2 / 3: row 0 / 1 present
+      int n_valid;            // statistics mode: live frames among this warp's 32 rows
+      long long part_idx;     //                  first element of this warp's 24 partial moments
     };
+    const bool stats_mode = p.out.cqt_part != nullptr;
     auto load_ctx = [&](int tile) {
       TileCtx c;
       int b, oct, t0;
@@ -471,6 +474,10 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
       const int t = t0 + quad * 32 + lane;
       c.off0 = c.off1 = 0;
       c.flags = 0;
+      c.n_valid = frames_b - (t0 + quad * 32);
+      c.n_valid = c.n_valid < 0 ? 0 : c.n_valid > 32 ? 32 : c.n_valid;
+      c.part_idx = ((((long long)b * kOctaves + oct) * p.tiles_per_clip_oct + t0 / kM) * 4 + quad) * kCqtCols;
+      if (stats_mode) return c;
       if (t < p.slots) {
         const RowDest d = row_dest(p.out, b, t, frames_b, sections_b);
         if (d.n > 0) c.off0 = (int)(d.row[0] - c.clip_out) + col0, c.flags |= 4 | (d.live[0] ? 1 : 0);
@@ -529,6 +536,22 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
       __syncwarp();
       TileCtx nxt = ctx;
       if (tile + stride2 < total) nxt = load_ctx(tile + stride2);
+      if (stats_mode) {
+        // compute_stats' per-clip reductions (compute_separated_stats.py:27-28) for this quadrant: lane c walks column
+        // c of the staged 32 x 24 block (Welford over the live rows) and leaves (mean, M2); nothing else is stored
+        if (lane < kCqtCols) {
+          float mean = 0.f, m2 = 0.f;
+          for (int r = 0; r < ctx.n_valid; ++r) {
+            const float x = stg[r * kEpiStride + lane], d = x - mean;
+            mean += d / (float)(r + 1);
+            m2 = fmaf(d, x - mean, m2);
+          }
+          p.out.cqt_part[ctx.part_idx + lane] = make_float2(mean, m2);
+        }
+        __syncwarp();
+        ctx = nxt;
+        continue;
+      }
       // 32 rows x 12 columns per plane = 12 store rounds; lane l of round i owns element 32 i + l
       float* const clip_out = ctx.clip_out;
 #pragma unroll

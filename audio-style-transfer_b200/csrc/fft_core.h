@@ -268,3 +268,83 @@ AST_HD float2 ihalf_pack(int tid, float2 xa, float2 xb) {
 }
 
 }  // namespace ast
+
+// ------------------------------------------------------------------------------------------------------------
+// 1024 = 32 x 32: one WARP per transform, 32 points per lane in registers, ONE exchange through a warp-private
+// shared-memory tile, no block-level barrier (stft.cu, istft.cu).
+//
+//   n = 32 n1 + n2 (n1: register, n2: lane)          k = k1 + 32 k2
+//   X[k1 + 32 k2] = sum_n2 W_32^(n2 k2) [ W_1024^(n2 k1) sum_n1 x[32 n1 + n2] W_32^(n1 k1) ]
+//   pass 1  lane n2: 32-point DFT over n1 -> A[k1], times W_1024^(n2 k1) -> tile[k1][n2]
+//   pass 2  lane k1: reads tile[k1][n2] over n2, 32-point DFT over n2 -> register k2 holds X[k1 + 32 k2]
+// Bins k and 1024 - k live in lanes k1 and (32 - k1) % 32, registers k2 and 31 - k2 (lane 0: 32 - k2): the Hermitian
+// separation of two real frames carried by one complex transform is one warp shuffle per bin.
+namespace ast {
+
+constexpr int kTileStride = 33;                  // float2 per tile row: conflict-free transposed reads
+constexpr int kTileSize = 32 * kTileStride;      // one warp's exchange tile (8448 B)
+constexpr int kTw32Size = 32 * 32;               // tw32[k1 * 32 + n2] = exp(-2 pi i n2 k1 / 1024)
+
+inline void fill_tw32(float2* tw) {
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int k1 = 0; k1 < 32; ++k1)
+    for (int n2 = 0; n2 < 32; ++n2) {
+      const double a = -two_pi * (double)(n2 * k1) / 1024.0;
+      tw[k1 * 32 + n2] = make_float2((float)cos(a), (float)sin(a));
+    }
+}
+
+// forward 32-point DFT in registers, natural order in and out: one radix-2 decimation-in-frequency step, then two
+// 16-point transforms (X[2m] from x[n] + x[n+16], X[2m+1] from (x[n] - x[n+16]) W_32^n)
+AST_HD void fft32(float2 (&v)[32]) {
+  // cos / sin of pi n / 16, n = 1..7
+  const float c1 = 0.98078528040323044913f, s1 = 0.19509032201612826785f;
+  const float c2 = 0.92387953251128673848f, s2 = 0.38268343236508978178f;
+  const float c3 = 0.83146961230254523708f, s3 = 0.55557023301960222474f;
+  const float r = 0.70710678118654752440f;
+  float2 a[16], b[16];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) {
+    a[n] = cadd(v[n], v[n + 16]);
+    b[n] = csub(v[n], v[n + 16]);
+  }
+  b[1] = cmul(b[1], make_float2(c1, -s1));
+  b[2] = cmul(b[2], make_float2(c2, -s2));
+  b[3] = cmul(b[3], make_float2(c3, -s3));
+  b[4] = cmul(b[4], make_float2(r, -r));
+  b[5] = cmul(b[5], make_float2(s3, -c3));
+  b[6] = cmul(b[6], make_float2(s2, -c2));
+  b[7] = cmul(b[7], make_float2(s1, -c1));
+  b[8] = mul_neg_i(b[8]);
+  b[9] = cmul(b[9], make_float2(-s1, -c1));
+  b[10] = cmul(b[10], make_float2(-s2, -c2));
+  b[11] = cmul(b[11], make_float2(-s3, -c3));
+  b[12] = cmul(b[12], make_float2(-r, -r));
+  b[13] = cmul(b[13], make_float2(-c3, -s3));
+  b[14] = cmul(b[14], make_float2(-c2, -s2));
+  b[15] = cmul(b[15], make_float2(-c1, -s1));
+  fft16(a);
+  fft16(b);
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    v[2 * m] = a[m];
+    v[2 * m + 1] = b[m];
+  }
+}
+
+// pass 1 of lane n2: v[n1] = z[32 n1 + n2] in, tile[k1][n2] out
+AST_HD void fft1024w_pass1(float2 (&v)[32], int lane, const float2* tw32, float2* tile) {
+  fft32(v);
+  tile[lane] = v[0];
+#pragma unroll
+  for (int k1 = 1; k1 < 32; ++k1) tile[k1 * kTileStride + lane] = cmul(v[k1], tw32[k1 * 32 + lane]);
+}
+
+// pass 2 of lane k1: v[k2] = Z[k1 + 32 k2] out (the caller synchronises the warp between the passes)
+AST_HD void fft1024w_pass2(float2 (&v)[32], int lane, const float2* tile) {
+#pragma unroll
+  for (int n2 = 0; n2 < 32; ++n2) v[n2] = tile[lane * kTileStride + n2];
+  fft32(v);
+}
+
+}  // namespace ast

@@ -124,4 +124,25 @@ void emul_irfft_pair(const float* xa, const float* xb, float* fa, float* fb) {
     fb[n] = -out[2 * n + 1] / kFftN;
   }
 }
+// the warp-per-transform 32 x 32 formulation (fft1024w_pass1 / pass2), lane by lane
+void emul_fft1024_warp(const float* in, float* out) {
+  std::vector<float2> tw(kTw32Size), tile(kTileSize);
+  fill_tw32(tw.data());
+  for (int lane = 0; lane < 32; ++lane) {
+    float2 v[32];
+    for (int n1 = 0; n1 < 32; ++n1) v[n1] = make_float2(in[2 * (32 * n1 + lane)], in[2 * (32 * n1 + lane) + 1]);
+    fft1024w_pass1(v, lane, tw.data(), tile.data());
+  }
+  for (int lane = 0; lane < 32; ++lane) {
+    float2 v[32];
+    fft1024w_pass2(v, lane, tile.data());
+    for (int k2 = 0; k2 < 32; ++k2) out[2 * (lane + 32 * k2)] = v[k2].x, out[2 * (lane + 32 * k2) + 1] = v[k2].y;
+  }
+}
+void emul_fft32(const float* in, float* out) {
+  float2 v[32];
+  for (int n = 0; n < 32; ++n) v[n] = make_float2(in[2 * n], in[2 * n + 1]);
+  fft32(v);
+  for (int n = 0; n < 32; ++n) out[2 * n] = v[n].x, out[2 * n + 1] = v[n].y;
+}
 }

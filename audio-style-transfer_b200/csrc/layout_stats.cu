@@ -11,15 +11,27 @@
 namespace ast {
 
 // ------------------------------------------------------------------------------------------
-__global__ void prep_stats_kernel(const float* __restrict__ mean, const float* __restrict__ std_, float eps, int n,
-                                  float2* __restrict__ table) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) table[i] = make_float2(mean[i], 1.0f / (std_[i] + eps));
+// table[i] = (mean, 1 / (std + eps)) for the CQT epilogue; stat4[row][k] = (-mean_re, -mean_im, rstd_re, rstd_im) of
+// STFT bin k: one 16-byte load per bin in the STFT kernel, already paired for its packed FP32x2 normalisation.  n = rows * 2 * 597.
+__device__ __forceinline__ void prep_stats_element(const float* __restrict__ mean, const float* __restrict__ std_, float eps,
+                                                   int i, float2* __restrict__ table, float4* __restrict__ stat4) {
+  table[i] = make_float2(mean[i], 1.0f / (std_[i] + eps));
+  const int row = i / (2 * kFTotal), r = i - row * 2 * kFTotal;
+  if (stat4 && r < kFStft) {
+    const int j = i + kFTotal;   // the channel-1 entry of the same bin
+    stat4[row * kStat4Stride + r] = make_float4(-mean[i], -mean[j], 1.0f / (std_[i] + eps), 1.0f / (std_[j] + eps));
+  }
 }
 
-int launch_prep_stats(const float* mean, const float* std_, float eps, int n, float2* table, cudaStream_t st) {
+__global__ void prep_stats_kernel(const float* __restrict__ mean, const float* __restrict__ std_, float eps, int n,
+                                  float2* __restrict__ table, float4* __restrict__ stat4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) prep_stats_element(mean, std_, eps, i, table, stat4);
+}
+
+int launch_prep_stats(const float* mean, const float* std_, float eps, int n, float2* table, float4* stat4, cudaStream_t st) {
   if (n == 0) return AST_OK;
-  prep_stats_kernel<<<(n + 255) / 256, 256, 0, st>>>(mean, std_, eps, n, table);
+  prep_stats_kernel<<<(n + 255) / 256, 256, 0, st>>>(mean, std_, eps, n, table, stat4);
   AST_LAUNCH_CHECK("prep_stats_kernel");
   return AST_OK;
 }
@@ -54,6 +66,7 @@ struct FeaturesPrologueParams {
   float eps;
   int n_stats;
   float2* table;
+  float4* stat4;
   const int32_t* lengths;
   int batch;
   long long max_samples;
@@ -71,7 +84,7 @@ __global__ void features_prologue_kernel(const FeaturesPrologueParams p) {
   const int stride = gridDim.x * blockDim.x;
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
   for (int i = i0; i < p.n_flags; i += stride) p.flags[i] = 0;
-  for (int i = i0; i < p.n_stats; i += stride) p.table[i] = make_float2(p.mean[i], 1.0f / (p.std_[i] + p.eps));
+  for (int i = i0; i < p.n_stats; i += stride) prep_stats_element(p.mean, p.std_, p.eps, i, p.table, p.stat4);
   if (p.n_out)
     for (int b = i0; b < p.batch; b += stride) {
       const int frames = num_frames(p.lengths ? p.lengths[b] : p.max_samples);
@@ -80,16 +93,16 @@ __global__ void features_prologue_kernel(const FeaturesPrologueParams p) {
     }
 }
 
-int launch_features_prologue(const float* mean, const float* std_, float eps, int n_stats, float2* table, const int32_t* lengths,
-                             int batch, long long max_samples, int layout, int dim1, int window, int overlap, int32_t* n_out,
-                             int* flags, int n_flags, cudaStream_t st) {
+int launch_features_prologue(const float* mean, const float* std_, float eps, int n_stats, float2* table, float4* stat4,
+                             const int32_t* lengths, int batch, long long max_samples, int layout, int dim1, int window,
+                             int overlap, int32_t* n_out, int* flags, int n_flags, cudaStream_t st) {
   int work = n_stats > n_flags ? n_stats : n_flags;
   if (n_out && batch > work) work = batch;
   if (work == 0) return AST_OK;
   int ctas = (work + 255) / 256;
   if (ctas > 1184) ctas = 1184;
-  const FeaturesPrologueParams p{mean, std_, eps, n_stats, table, lengths, batch, max_samples, layout, dim1, window, overlap,
-                                 n_out, flags, n_flags};
+  const FeaturesPrologueParams p{mean, std_, eps, n_stats, table, stat4, lengths, batch, max_samples, layout, dim1, window,
+                                 overlap, n_out, flags, n_flags};
   ProfileSpan span("features_prologue_kernel", st);
   AST_CUDA_TRY(launch_with_pdl(features_prologue_kernel, dim3((unsigned)ctas), 256, 0, st, p));
   return AST_OK;
@@ -212,6 +225,59 @@ int launch_clip_stats(const float* feats, const int32_t* n_frames, int batch, in
   ProfileSpan span("clip_stats_kernel", st);
   clip_stats_kernel<<<grid, kStatCols * kStatSlices, 0, st>>>(feats, n_frames, t_dim, f_dim, clip_stats);
   AST_LAUNCH_CHECK("clip_stats_kernel");
+  return AST_OK;
+}
+
+// K6 fused, part 1b: the feature kernels in statistics mode leave per-tile (mean, M2) partials instead of features
+// (stft.cu: one per CTA tile of frames; cqt_tc.cu: one per 32-frame quadrant of a 128-frame tile).  One CTA per clip
+// merges them in frame order with Chan's formula in float64 and writes the clip's mean and UNBIASED variance
+// (compute_separated_stats.py:27-28) in the layout stats_accumulate_kernel adds up.
+__global__ void __launch_bounds__(256) stats_finalize_clips_kernel(const float2* __restrict__ part_stft,
+                                                                   const float* __restrict__ part_n, int stft_tiles,
+                                                                   const float2* __restrict__ part_cqt, int cqt_tiles,
+                                                                   const int32_t* __restrict__ lengths, long long max_samples,
+                                                                   double* __restrict__ clip_stats) {
+  const int b = blockIdx.x;
+  const int frames = num_frames(lengths ? lengths[b] : max_samples);
+  for (int idx = threadIdx.x; idx < 2 * kFTotal; idx += blockDim.x) {
+    const int c = idx / kFTotal, f = idx - c * kFTotal;
+    double n = 0.0, mean = 0.0, m2 = 0.0;
+    auto merge = [&](double nb, float2 pm) {
+      if (nb <= 0.0) return;
+      const double nn = n + nb, d = (double)pm.x - mean;
+      mean += d * nb / nn;
+      m2 += (double)pm.y + d * d * n * nb / nn;
+      n = nn;
+    };
+    if (f < kFStft) {
+      for (int i = 0; i < stft_tiles; ++i) {
+        const long long tile = (long long)b * stft_tiles + i;
+        merge((double)part_n[tile], part_stft[(tile * 2 + c) * kFStft + f]);
+      }
+    } else {
+      const int j = f - kFStft, oct = kOctaves - 1 - j / kBinsPerOctave;
+      const int col = j % kBinsPerOctave + c * kBinsPerOctave;
+      for (int i = 0; i < cqt_tiles; ++i)
+        for (int q = 0; q < 4; ++q) {
+          int nb = frames - (i * 128 + q * 32);
+          nb = nb < 0 ? 0 : nb > 32 ? 32 : nb;
+          merge((double)nb, part_cqt[((((long long)b * kOctaves + oct) * cqt_tiles + i) * 4 + q) * kCqtCols + col]);
+        }
+    }
+    double* o = clip_stats + (long long)b * 4 * kFTotal;
+    o[c * kFTotal + f] = mean;
+    o[(2 + c) * kFTotal + f] = frames > 1 ? m2 / (frames - 1) : 0.0;   // torch.std(dim=1) is unbiased
+  }
+}
+
+int launch_stats_finalize_clips(const float2* part_stft, const float* part_n, int stft_tiles, const float2* part_cqt,
+                                int cqt_tiles, const int32_t* lengths, long long max_samples, int batch, double* clip_stats,
+                                cudaStream_t st) {
+  if (batch == 0) return AST_OK;
+  ProfileSpan span("stats_finalize_clips_kernel", st);
+  stats_finalize_clips_kernel<<<batch, 256, 0, st>>>(part_stft, part_n, stft_tiles, part_cqt, cqt_tiles, lengths, max_samples,
+                                                     clip_stats);
+  AST_LAUNCH_CHECK("stats_finalize_clips_kernel");
   return AST_OK;
 }
 

@@ -311,6 +311,11 @@ int ast_plan_create(const ast_config* cfg, ast_plan** out) {
   } while (0)
   AST_ALLOC_COPY(p->d_tw1, tw1.data(), sizeof(float2) * kTw1Size);
   AST_ALLOC_COPY(p->d_tw2, tw2.data(), sizeof(float2) * kTw2Size);
+  {
+    std::vector<float2> tw32(kTw32Size);
+    fill_tw32(tw32.data());
+    AST_ALLOC_COPY(p->d_tw32, tw32.data(), sizeof(float2) * kTw32Size);
+  }
   AST_ALLOC_COPY(p->d_hann, w.data(), sizeof(float) * kNfft);
   AST_ALLOC_COPY(p->d_hann_inv_n, w_inv.data(), sizeof(float) * kNfft);
   AST_ALLOC_COPY(p->d_hann_sq, w_sq.data(), sizeof(float) * kNfft);
@@ -358,6 +363,7 @@ int ast_plan_destroy(ast_plan* p) {
   if (!p) return AST_OK;
   cudaFree(p->d_tw1);
   cudaFree(p->d_tw2);
+  cudaFree(p->d_tw32);
   cudaFree(p->d_hann);
   cudaFree(p->d_hann_inv_n);
   cudaFree(p->d_hann_sq);

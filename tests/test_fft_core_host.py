@@ -64,3 +64,30 @@ def test_real_pair_inverse(emul):
     rb = np.fft.irfft(xb.astype(np.complex128), n=1024)
     scale = max(np.abs(ra).max(), np.abs(rb).max())
     assert np.abs(fa - ra).max() < 2e-6 * scale and np.abs(fb - rb).max() < 2e-6 * scale
+
+
+def test_warp_formulation_32x32(emul):
+    """fft32 and the one-warp 1024-point transform (32 points per lane, one exchange tile) used by stft.cu / istft.cu."""
+    rng = np.random.default_rng(3)
+    z = (rng.standard_normal(32) + 1j * rng.standard_normal(32)).astype(np.complex64)
+    out = np.zeros(32, dtype=np.complex64)
+    emul.emul_fft32(_p(z), _p(out))
+    ref = np.fft.fft(z.astype(np.complex128))
+    assert np.abs(out - ref).max() < 1e-6 * np.abs(ref).max()
+    z = (rng.standard_normal(1024) + 1j * rng.standard_normal(1024)).astype(np.complex64)
+    out = np.zeros(1024, dtype=np.complex64)
+    emul.emul_fft1024_warp(_p(z), _p(out))
+    ref = np.fft.fft(z.astype(np.complex128))
+    assert np.abs(out - ref).max() < 2e-6 * np.abs(ref).max()
+    # two real frames in one transform: bins k and N - k separate exactly, imag DC / Nyquist exactly 0
+    fa, fb = rng.standard_normal(1024).astype(np.float32), rng.standard_normal(1024).astype(np.float32)
+    zz = (fa + 1j * fb).astype(np.complex64)
+    emul.emul_fft1024_warp(_p(zz), _p(out))
+    k = np.arange(513)
+    zk, zp = out[k], out[(1024 - k) % 1024]
+    xa = 0.5 * ((zk.real + zp.real) + 1j * (zk.imag - zp.imag))
+    xb = 0.5 * ((zk.imag + zp.imag) + 1j * (zp.real - zk.real))
+    ra, rb = np.fft.rfft(fa.astype(np.float64)), np.fft.rfft(fb.astype(np.float64))
+    scale = max(np.abs(ra).max(), np.abs(rb).max())
+    assert np.abs(xa - ra).max() < 2e-6 * scale and np.abs(xb - rb).max() < 2e-6 * scale
+    assert xa.imag[0] == 0 and xa.imag[512] == 0 and xb.imag[0] == 0 and xb.imag[512] == 0
