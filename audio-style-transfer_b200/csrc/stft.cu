@@ -97,22 +97,30 @@ __device__ __forceinline__ void frame_rows(const OutSpec& o, int b, int t, int f
 // Normalisation runs on the packed FP32x2 pipe: (re, im) of a frame against (-mean_re, -mean_im) and (rstd_re, rstd_im).
 // Values arrive WITHOUT the factor 1/2 of the Hermitian separation; x = 0.5 s is exact, so fma(s, 0.5, -mean) rounds
 // once, exactly like the reference's (x - mean).
+// (-mean_re, -mean_im, rstd_re, rstd_im) of one bin against both frames of the pair
+__device__ __forceinline__ void normalise_pair(float2& a, float2& b, const float4& s) {
+#if defined(__CUDA_ARCH__)
+  const float2 half = make_float2(0.5f, 0.5f);
+  a = __fmul2_rn(__ffma2_rn(a, half, make_float2(s.x, s.y)), make_float2(s.z, s.w));
+  b = __fmul2_rn(__ffma2_rn(b, half, make_float2(s.x, s.y)), make_float2(s.z, s.w));
+#endif
+}
+struct StftStats {   // the per-bin table of a clip, or none (raw features: x = 0.5 s)
+  const float4* st;  // pre-offset by the lane; nullptr: raw
+  __device__ __forceinline__ float4 operator()(int k) const {
+    return st ? __ldg(st + k) : make_float4(0.f, 0.f, 1.f, 1.f);
+  }
+};
+
 template <int kRows>
 struct StftStore {
   float *a0r, *a0i, *a1r, *a1i, *b0r, *b0i, *b1r, *b1i;   // nullptr: absent
   bool la0, la1, lb0, lb1;
-  const float4* st;     // per-bin (-mean_re, -mean_im, rstd_re, rstd_im), pre-offset by the lane; nullptr: raw
-  __device__ __forceinline__ void operator()(int k, float2 a, float2 b) const {
-    const float2 half = make_float2(0.5f, 0.5f);
-#if defined(__CUDA_ARCH__)
-    if (st) {
-      const float4 s = __ldg(st + k);
-      a = __fmul2_rn(__ffma2_rn(a, half, make_float2(s.x, s.y)), make_float2(s.z, s.w));
-      b = __fmul2_rn(__ffma2_rn(b, half, make_float2(s.x, s.y)), make_float2(s.z, s.w));
-    } else {
-      a = __fmul2_rn(a, half);
-      b = __fmul2_rn(b, half);
-    }
+  StftStats stat;
+  __device__ __forceinline__ void operator()(int k, float2 a, float2 b, const float4& s) const {
+    normalise_pair(a, b, s);
+#ifdef AST_STFT_NOSTORE   // diagnostic build (scratch/build_variant.sh): the arithmetic stays, (almost) nothing is stored
+    if (a.x != 1.2345e30f) return;
 #endif
     if (kRows == 1) {
       a0r[k] = a.x, a0i[k] = a.y, b0r[k] = b.x, b0i[k] = b.y;
@@ -128,6 +136,51 @@ struct StftStore {
   }
 };
 
+// The common case goes through shared memory and the bulk-copy (TMA) engine: output rows start on 4-byte boundaries
+// only, so a warp-wide scalar store covers 128 bytes across two lines and five sectors, two of them partial, and the
+// 91 such stores of a pair were the kernel's largest single cost (35 of 124 us per 64 clips, measured by predicating them
+// off).  Instead the four row-planes of a pair (A re, A im, B re, B im; 513 floats each) are staged in the warp's
+// exchange tile, each shifted by its destination's phase (address / 4 mod 4) so that the 16-byte-aligned body of the
+// row is 16-byte aligned in shared memory too, and written by ONE cp.async.bulk per row-plane (2 032 - 2 048 bytes);
+// the <= 3 floats of head and tail go out as scalar stores.  Second rows of frames inside a section overlap have a
+// different phase and are stored the plain way (kDup).
+constexpr int kStageRow = 516;   // floats per staged row-plane: 513 + up to 3 of phase shift
+template <bool kDup>
+struct StftStage {
+  float *s0, *s1, *s2, *s3;          // staged rows A re, A im, B re, B im; pre-offset by phase + lane
+  float *a1r, *a1i, *b1r, *b1i;      // kDup: the frames' second rows, pre-offset by the lane
+  StftStats stat;
+  __device__ __forceinline__ void operator()(int k, float2 a, float2 b, const float4& s) const {
+    normalise_pair(a, b, s);
+    s0[k] = a.x, s1[k] = a.y, s2[k] = b.x, s3[k] = b.y;
+    if (kDup) a1r[k] = a.x, a1i[k] = a.y, b1r[k] = b.x, b1i[k] = b.y;
+  }
+};
+
+__device__ __forceinline__ void bulk_store(float* gmem, const float* smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem),
+               "r"((uint32_t)__cvta_generic_to_shared(smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// The four staged row-planes -> their destination rows.  Lane j < 4 issues the bulk copy of row-plane j (one
+// instruction, four copies); lanes 8 j + i, i < 6, carry the <= 3 head and <= 3 tail floats of row-plane j.
+__device__ __forceinline__ void flush_rows(float* const (&rows)[4], const float* __restrict__ stage, const int (&ph)[4], int lane) {
+  const int j = (lane >> 3) & 3, i = lane & 7;
+  float* row = j == 0 ? rows[0] : j == 1 ? rows[1] : j == 2 ? rows[2] : rows[3];
+  const int phase = j == 0 ? ph[0] : j == 1 ? ph[1] : j == 2 ? ph[2] : ph[3];
+  const float* staged = stage + j * kStageRow + phase;
+  const int head = (4 - phase) & 3;                  // floats before the first 16-byte boundary
+  const int body = (kFStft - head) & ~3;             // 508 or 512 floats
+  const int tail = kFStft - head - body;
+  const int e = i < 3 ? i : head + body + (i - 3);
+  if (i < 6 && (i < 3 ? i < head : i - 3 < tail)) row[e] = staged[e];
+  if (i == 7) bulk_store(row + head, staged + head, (uint32_t)body * 4u);
+}
+
 // Statistics mode: running (mean, M2) per bin and channel over the frames this warp has seen, in the warp's own
 // shared-memory array (each lane owns its bins: no conflicts, no atomics).  A pair enters as its own two-sample
 // (mean, M2) and is merged with Chan's formula; w1 = cnt / n, w2 = n_prev cnt / n are warp-uniform.
@@ -135,7 +188,8 @@ struct StftMoments {
   float4* acc;   // [516] (mean_re, M2_re, mean_im, M2_im), pre-offset by the lane
   float w1, w2;
   bool two;      // both frames of the pair are live
-  __device__ __forceinline__ void operator()(int k, float2 a, float2 b) const {
+  StftStats stat;
+  __device__ __forceinline__ void operator()(int k, float2 a, float2 b, const float4&) const {
     const float are = 0.5f * a.x, aim = 0.5f * a.y, bre = 0.5f * b.x, bim = 0.5f * b.y;
     float4 s = acc[k];
     float mre = are, mim = aim, qre = 0.f, qim = 0.f;
@@ -157,24 +211,104 @@ struct StftMoments {
 // emit(k, (A_re, A_im), (B_re, B_im)), both without the factor 1/2:
 //   A[k] = Z[k] + conj Z[N - k]          B[k] = -i (Z[k] - conj Z[N - k])
 template <class Emit>
-__device__ __forceinline__ void separate_and_emit(const float2 (&v)[32], int lane, const Emit& emit) {
+__device__ __forceinline__ void separate_and_emit(float2 (&v)[32], int lane, const Emit& emit) {
+  // Z[1024 - k] of bin k = lane + 32 k2 lives in lane (32 - lane) % 32, register 31 - k2 (lane 0: its own register
+  // (32 - k2) % 32).  (AST_STFT_EMIT_BATCH: all 32 shuffles first, in place, statistics fetched four bins at a time -
+  // measured slower: the longer live ranges spill at the 128-register cap.)
   const int src = (32 - lane) & 31;
+#if defined(AST_STFT_EMIT_BATCH)
+#pragma unroll
+  for (int j = 16; j < 32; ++j) {
+    v[j].x = __shfl_sync(0xffffffffu, v[j].x, src);
+    v[j].y = __shfl_sync(0xffffffffu, v[j].y, src);
+  }
+  // bins in batches of four: the batch's per-bin statistics are fetched together, ahead of its arithmetic
+#pragma unroll
+  for (int kb = 0; kb < 16; kb += 4) {
+    float4 st[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st[j] = emit.stat(32 * (kb + j));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k2 = kb + j;
+      float2 zp = v[31 - k2];
+      if (lane == 0) zp = v[(32 - k2) & 31];   // (lane 0 shuffled with itself: registers unchanged)
+      const float2 a = cadd(v[k2], make_float2(zp.x, -zp.y));
+      const float2 d = csub(v[k2], make_float2(zp.x, -zp.y));
+      emit(32 * k2, a, make_float2(d.y, -d.x), st[j]);
+    }
+  }
+#else
 #pragma unroll
   for (int k2 = 0; k2 < 16; ++k2) {
-    // Z[1024 - k]: lane (32 - k1) % 32, register 31 - k2; lane 0 pairs with its own register (32 - k2) % 32
     float2 zp;
     zp.x = __shfl_sync(0xffffffffu, v[31 - k2].x, src);
     zp.y = __shfl_sync(0xffffffffu, v[31 - k2].y, src);
     if (lane == 0) zp = v[(32 - k2) & 31];
     const float2 a = cadd(v[k2], make_float2(zp.x, -zp.y));
     const float2 d = csub(v[k2], make_float2(zp.x, -zp.y));
-    emit(32 * k2, a, make_float2(d.y, -d.x));
+    emit(32 * k2, a, make_float2(d.y, -d.x), emit.stat(32 * k2));
   }
+#endif
   if (lane == 0) {  // bin 512 is its own conjugate partner: imaginary parts exactly 0
     const float2 zk = v[16];
-    emit(512, make_float2(zk.x + zk.x, zk.y - zk.y), make_float2(zk.y + zk.y, zk.x - zk.x));
+    emit(512, make_float2(zk.x + zk.x, zk.y - zk.y), make_float2(zk.y + zk.y, zk.x - zk.x), emit.stat(512));
   }
 }
+
+// periodic Hann w[32 i + lane] from the lane's (cos theta, sin theta), theta = 2 pi lane / 1024; i is a compile-time
+// constant after unrolling, so the two coefficients are immediates: two FFMA, no load
+__device__ __forceinline__ float hann_at(int i, float cos_t, float sin_t) {
+  // -0.5 cos(2 pi i / 32) and 0.5 sin(2 pi i / 32), i = 0..31 (literals: the device compiler does not fold cos())
+  constexpr float kC[32] = {
+      -0.5f, -0.49039264f, -0.461939766f, -0.415734806f,
+      -0.353553391f, -0.277785117f, -0.191341716f, -0.097545161f,
+      0.f, 0.097545161f, 0.191341716f, 0.277785117f,
+      0.353553391f, 0.415734806f, 0.461939766f, 0.49039264f,
+      0.5f, 0.49039264f, 0.461939766f, 0.415734806f,
+      0.353553391f, 0.277785117f, 0.191341716f, 0.097545161f,
+      0.f, -0.097545161f, -0.191341716f, -0.277785117f,
+      -0.353553391f, -0.415734806f, -0.461939766f, -0.49039264f,
+  };
+  constexpr float kS[32] = {
+      0.f, 0.097545161f, 0.191341716f, 0.277785117f,
+      0.353553391f, 0.415734806f, 0.461939766f, 0.49039264f,
+      0.5f, 0.49039264f, 0.461939766f, 0.415734806f,
+      0.353553391f, 0.277785117f, 0.191341716f, 0.097545161f,
+      0.f, -0.097545161f, -0.191341716f, -0.277785117f,
+      -0.353553391f, -0.415734806f, -0.461939766f, -0.49039264f,
+      -0.5f, -0.49039264f, -0.461939766f, -0.415734806f,
+      -0.353553391f, -0.277785117f, -0.191341716f, -0.097545161f,
+  };
+  return fmaf(kC[i], cos_t, fmaf(kS[i], sin_t, 0.5f));
+}
+
+#ifdef AST_STFT_TRACE
+// diagnostic build only (scratch/trace_stft.py): cycles per phase of a pair, summed per warp of the first CTAs
+__device__ long long g_stft_trace[64][8];
+#define STFT_STAMP(k)                                                                 \
+  do {                                                                                \
+    if (kMode == 0 && lane == 0 && blockIdx.y == 0 && blockIdx.x < 16) {              \
+      const long long now_ = clock64();                                               \
+      g_stft_trace[blockIdx.x * kStftWarps + warp][k] += now_ - t_prev_;              \
+      t_prev_ = now_;                                                                 \
+    }                                                                                 \
+  } while (0)
+__device__ unsigned long long g_stft_cta_ns[4096][3];   // start, end (globaltimer), SM id per CTA (linear block id)
+extern "C" int ast_debug_stft_trace(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, g_stft_trace, sizeof(long long) * 64 * 8);
+}
+extern "C" int ast_debug_stft_cta_times(unsigned long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, g_stft_cta_ns, sizeof(unsigned long long) * 4096 * 3);
+}
+__device__ __forceinline__ unsigned long long stft_global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#else
+#define STFT_STAMP(k) do {} while (0)
+#endif
 
 template <int kMode>   // 0: features (normalise + store), 1: statistics (per-bin moments, nothing stored)
 __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 2) stft_kernel(const StftParams p) {
@@ -190,14 +324,28 @@ __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 2) 
   const int sections_b = p.out.layout == AST_LAYOUT_SECTIONS ? num_sections(frames_b, p.out.window, p.overlap) : 0;
   const float* __restrict__ x = p.wave + (long long)b * p.wave_stride;
   const float2* __restrict__ tw = p.tw32;
-  const float* __restrict__ win = p.hann + lane;
   const float4* st = p.stat4 ? p.stat4 + (long long)b * p.stat4_clip_stride + lane : nullptr;
   const long long plane = (long long)(p.out.layout == AST_LAYOUT_FLAT ? p.out.dim1 : p.out.window) * p.out.f_row;
   float n_acc = 0.f;
   if (kMode == 1)
     for (int k = lane; k < kAccStride; k += 32) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
+  // Hann from the lane's rotation: w[32 i + lane] = 0.5 - 0.5 cos(2 pi i / 32 + theta), theta = 2 pi lane / 1024, expanded
+  // with the compile-time cos / sin of 2 pi i / 32 against (cos theta, sin theta) = conj(W_1024^lane): two FFMA, no load
+  const float2 w1 = __ldg(tw + 32 + lane);
+  const float cos_t = w1.x, sin_t = -w1.y;
+#ifdef AST_STFT_TRACE
+  long long t_prev_ = clock64();
+  const unsigned cta_lin_ = blockIdx.x + gridDim.x * blockIdx.y;
+  if (kMode == 0 && threadIdx.x == 0 && cta_lin_ < 4096) {
+    unsigned smid_;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid_));
+    g_stft_cta_ns[cta_lin_][0] = stft_global_ns();
+    g_stft_cta_ns[cta_lin_][2] = smid_;
+  }
+#endif
   for (int it = 0; it < p.iters; ++it) {
+    STFT_STAMP(0);   // loop overhead / previous pair's tail
     const int pair = (blockIdx.x * p.iters + it) * kStftWarps + warp;
     if (pair >= p.pairs_per_clip) break;   // warp-uniform; nothing below synchronises across warps
     const int ta = 2 * pair;
@@ -211,13 +359,28 @@ __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 2) 
         float xv[40];
 #pragma unroll
         for (int i = 0; i < 40; ++i) xv[i] = __ldg(xp + 32 * i);
+#ifndef AST_STFT_PF
+#define AST_STFT_PF 1
+#endif
+#if AST_STFT_PF == 1
         // this warp's next pair starts kStftWarps x 512 samples further; its first 768 samples are being read by the
         // CTA's other warps right now, the last 512 (16 lines) are new: one line per lane into the L1
         if (it + 1 < p.iters && lane < 16 && (ta + 2 * kStftWarps + 1) * kHop + kNfft / 2 <= len)
           asm volatile("prefetch.global.L1 [%0];" ::"l"(xp + 2 * kStftWarps * kHop + 768 - lane + 32 * lane));
+#elif AST_STFT_PF == 2
+        if (it + 1 < p.iters && (ta + 2 * kStftWarps + 1) * kHop + kNfft / 2 <= len) {
+          const float* xn = xp - lane + 2 * kStftWarps * kHop;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(xn + 32 * lane));
+          if (lane < 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(xn + 32 * (32 + lane)));
+        }
+#endif
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float w = __ldg(win + 32 * i);
+#if !defined(AST_STFT_WIN_COMPUTED)
+          const float w = __ldg(p.hann + lane + 32 * i);
+#else
+          const float w = hann_at(i, cos_t, sin_t);
+#endif
 #if defined(__CUDA_ARCH__)
           v[i] = __fmul2_rn(make_float2(xv[i], xv[i + 8]), make_float2(w, w));
 #endif
@@ -226,26 +389,60 @@ __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 2) 
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int idx = base + 32 * i;
-          const float w = __ldg(win + 32 * i);
+#if !defined(AST_STFT_WIN_COMPUTED)
+          const float w = __ldg(p.hann + lane + 32 * i);
+#else
+          const float w = hann_at(i, cos_t, sin_t);
+#endif
           const float xa = load_reflect(x, idx, len, p.pad_zero);
           const float xb = live_b ? load_reflect(x, idx + kHop, len, p.pad_zero) : 0.f;
           v[i] = make_float2(xa * w, xb * w);
         }
       }
+      STFT_STAMP(1);   // sample loads + window
+#ifndef AST_STFT_NOFFT    // diagnostic build: loads, exchange and stores without the two in-register transforms
       fft32(v);
+#endif
+      STFT_STAMP(2);   // first transform
+      if (kMode == 0) {   // the previous pair's bulk stores have read the tile they were staged in
+        bulk_wait_read();   // (every lane: bulk groups are per thread, lanes 7 / 15 / 23 / 31 issued the copies)
+        __syncwarp();
+      }
       tile[lane] = v[0];
+      {
+        // the twiddle W_1024^(lane k1) that follows pass 1, from ten table entries instead of 31:
+        // wb[b] = W^(lane b), b = 1..7; wa[a] = W^(8 a lane), a = 1..3; W^(lane k1) = wa[k1 / 8] wb[k1 % 8]
+        // (one multiplication of two correctly rounded entries: one more rounding than a direct table entry)
+#if !defined(AST_STFT_TW_LADDER)
 #pragma unroll
-      for (int k1 = 1; k1 < 32; ++k1) tile[k1 * kTileStride + lane] = cmul(v[k1], __ldg(tw + k1 * 32 + lane));
+        for (int k1 = 1; k1 < 32; ++k1) tile[k1 * kTileStride + lane] = cmul(v[k1], __ldg(tw + k1 * 32 + lane));
+#else
+        float2 wb[8], wa[4];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) wb[i] = __ldg(tw + i * 32 + lane);
+#pragma unroll
+        for (int i = 1; i < 4; ++i) wa[i] = __ldg(tw + 8 * i * 32 + lane);
+#pragma unroll
+        for (int k1 = 1; k1 < 32; ++k1) {
+          const float2 w = (k1 & 7) == 0 ? wa[k1 >> 3] : k1 < 8 ? wb[k1] : cmul(wa[k1 >> 3], wb[k1 & 7]);
+          tile[k1 * kTileStride + lane] = cmul(v[k1], w);
+        }
+#endif
+      }
       __syncwarp();
 #pragma unroll
       for (int n2 = 0; n2 < 32; ++n2) v[n2] = tile[lane * kTileStride + n2];
       __syncwarp();   // the tile may be rewritten by the next pair
+      STFT_STAMP(3);   // twiddle + exchange
+#ifndef AST_STFT_NOFFT
       fft32(v);
+#endif
+      STFT_STAMP(4);   // second transform
     }
     if (kMode == 1) {
       if (any_live) {
         const float cnt = live_b ? 2.f : 1.f, n_new = n_acc + cnt;
-        const StftMoments emit{acc + lane, cnt / n_new, n_acc * cnt / n_new, live_b};
+        const StftMoments emit{acc + lane, cnt / n_new, n_acc * cnt / n_new, live_b, StftStats{nullptr}};
         separate_and_emit(v, lane, emit);
         n_acc = n_new;
       }
@@ -257,22 +454,53 @@ __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 2) 
     if (ta + 1 < p.slots) frame_rows(p.out, b, ta + 1, frames_b, sections_b, b0, b1, lb0, lb1);
     auto re = [&](float* r) { return r ? r + lane : nullptr; };
     auto im = [&](float* r) { return r ? r + lane + plane : nullptr; };
+#ifndef AST_STFT_PLAIN_STORES
+    const bool single = !a1 && !b1, dup = la1 && lb1;
+    if (any_live && la0 && lb0 && (single || dup)) {
+      float* stage = reinterpret_cast<float*>(tile);   // free: pass 2 has read it (and the warp has synchronised)
+      float* rows[4] = {a0, a0 + plane, b0, b0 + plane};
+      int ph[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ph[j] = (int)((reinterpret_cast<uintptr_t>(rows[j]) >> 2) & 3);
+      float* s0 = stage + ph[0] + lane;
+      float* s1 = stage + kStageRow + ph[1] + lane;
+      float* s2 = stage + 2 * kStageRow + ph[2] + lane;
+      float* s3 = stage + 3 * kStageRow + ph[3] + lane;
+      if (single) {
+        const StftStage<false> emit{s0, s1, s2, s3, nullptr, nullptr, nullptr, nullptr, StftStats{st}};
+        separate_and_emit(v, lane, emit);
+      } else {
+        const StftStage<true> emit{s0, s1, s2, s3, re(a1), im(a1), re(b1), im(b1), StftStats{st}};
+        separate_and_emit(v, lane, emit);
+      }
+      STFT_STAMP(5);   // separation + normalisation + staging
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the bulk-copy engine
+      __syncwarp();
+      flush_rows(rows, stage, ph, lane);
+      bulk_commit();   // (per thread: lanes 7, 15, 23, 31 have one copy each in their group, the others an empty one)
+      STFT_STAMP(6);   // fence + flush
+    } else
+#endif
     if (any_live && la0 && lb0 && !a1 && !b1) {
-      const StftStore<1> emit{re(a0), im(a0), nullptr, nullptr, re(b0), im(b0), nullptr, nullptr, true, false, true, false, st};
+      const StftStore<1> emit{re(a0), im(a0), nullptr, nullptr, re(b0), im(b0), nullptr, nullptr, true, false, true, false, StftStats{st}};
       separate_and_emit(v, lane, emit);
     } else if (any_live && la0 && lb0 && la1 && lb1) {
-      const StftStore<2> emit{re(a0), im(a0), re(a1), im(a1), re(b0), im(b0), re(b1), im(b1), true, true, true, true, st};
+      const StftStore<2> emit{re(a0), im(a0), re(a1), im(a1), re(b0), im(b0), re(b1), im(b1), true, true, true, true, StftStats{st}};
       separate_and_emit(v, lane, emit);
     } else if (any_live) {
-      const StftStore<0> emit{re(a0), im(a0), re(a1), im(a1), re(b0), im(b0), re(b1), im(b1), la0, la1, lb0, lb1, st};
+      const StftStore<0> emit{re(a0), im(a0), re(a1), im(a1), re(b0), im(b0), re(b1), im(b1), la0, la1, lb0, lb1, StftStats{st}};
       separate_and_emit(v, lane, emit);
     } else {
       // both frames lie past the clip: their rows exist in the output and must be zeros
-      const StftStore<0> emit{re(a0), im(a0), re(a1), im(a1), re(b0), im(b0), re(b1), im(b1), false, false, false, false, nullptr};
-      for (int k = 0; k + lane < kFStft; k += 32) emit(k, make_float2(0.f, 0.f), make_float2(0.f, 0.f));
+      const StftStore<0> emit{re(a0), im(a0), re(a1), im(a1), re(b0), im(b0), re(b1), im(b1), false, false, false, false, StftStats{nullptr}};
+      for (int k = 0; k + lane < kFStft; k += 32) emit(k, make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float4(0.f, 0.f, 1.f, 1.f));
     }
   }
 
+  if (kMode == 0) bulk_wait_all();   // shared memory must outlive the bulk copies that read it
+#ifdef AST_STFT_TRACE
+  if (kMode == 0 && threadIdx.x == 0 && cta_lin_ < 4096) g_stft_cta_ns[cta_lin_][1] = stft_global_ns();
+#endif
   if (kMode == 1) {
     // merge the CTA's warps (frame-ascending interleave does not matter to Chan's formula) in double and write the
     // tile's partial moments; the finalise kernel merges tiles in order
