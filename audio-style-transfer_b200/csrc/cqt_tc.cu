@@ -27,10 +27,16 @@
 // (x - mean) * rstd, and stores to the flat / section layout (columns 513..596).
 //
 // One persistent CTA per SM, 16 warps:
-//   warps 0-5   producers: global -> registers -> hi / lo split -> shared A block (4-stage ring, mbarrier full / empty);
-//               two groups of three warps take alternate blocks: fence.proxy.async waits for a thread's outstanding
-//               loads, so a group issues the loads of its NEXT block right after publishing one and does not fence
-//               again until the other group's block has gone by
+//   warp  6     TMA: one thread walks the CTA's block sequence; per block it waits for the decimator tiles the block
+//               reads (completion counters) and for a free raw stage, then issues ONE cp.async.bulk.tensor.3d - a box of
+//               (32 samples, 128..191 rows, 1 clip) out of a per-octave tensor map whose row stride is the octave's hop,
+//               so the box IS the block's chunk columns; rows before the clip (and past the map) arrive as zeros
+//   warps 0-5   splitters: raw stage (row-major, as TMA wrote it) -> hi / lo split -> chunk-column A block of the 3-stage
+//               operand ring.  Two groups of three warps take alternate blocks (group g owns raw stage g).  Round 1's
+//               producers fetched the samples themselves (LDG -> registers): a thread's fence.proxy.async and
+//               releasing mbarrier.arrive wait for its outstanding loads, which exposed ~ 34 us of load latency per
+//               64 clips; with the loads on the TMA engine the splitters touch shared memory only.  (Inputs whose
+//               rows are not 16-byte aligned cannot be described by a tensor map: they keep the register path.)
 //   warps 8-15  epilogue : TMEM -> registers -> shared transpose -> global; two groups of four warps (one TMEM lane
 //               quadrant each) take alternate tiles, i.e. one accumulator set each - the epilogue, not the tensor
 //               pipe, is the longest stage of a tile (scratch/trace_cqt.py, scratch/dbg_cqt.sh)
@@ -38,6 +44,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -49,11 +57,20 @@ constexpr int kN = 32;                  // 24 outputs padded to 32
 constexpr int kKSteps = 32;             // 256-sample window / 8
 constexpr int kGroupThreads = 96;       // producer group: three warps (a multiple of 8 and of every m < 8)
 constexpr int kProducerWarps = 6;       // two groups, warps 0-2 and 3-5, alternate blocks
-constexpr int kMmaWarp = 7;             // (warp 6 idles: 16 warps keep four per scheduler, i.e. 128 registers per thread)
+constexpr int kTmaWarp = 6;             // one thread: tensor-map loads into the raw ring
+constexpr int kMmaWarp = 7;
 constexpr int kEpilogueWarp0 = 8;       // warps 8-11: even tiles, warps 12-15: odd tiles
 constexpr int kThreads = 16 * 32;       // 4 warps per scheduler: 128 registers per thread
 constexpr int kBlockCols = 8;                             // chunk columns per block (32 samples of every row)
-constexpr int kStages = 4;                                // ring of staged blocks
+#ifndef AST_CQT_STAGES
+#define AST_CQT_STAGES 2
+#endif
+#ifndef AST_CQT_RAW_STAGES
+#define AST_CQT_RAW_STAGES 4
+#endif
+constexpr int kStages = AST_CQT_STAGES;                   // ring of staged operand blocks (hi + lo)
+constexpr int kRawStages = AST_CQT_RAW_STAGES;            // ring of raw blocks as TMA delivers them (two per splitter group:
+                                                          // the box of a group's next block is in flight while it splits one)
 constexpr int kMaxBlockChunks = 8 * 135;                  // octave 3: the largest block, 1080 chunks
 constexpr int kAFloats = kMaxBlockChunks * 4;             // 4320 floats = 17 280 B per split term
 constexpr int kStageFloats = 2 * kAFloats;                // hi + lo
@@ -65,7 +82,7 @@ constexpr int kTmemCols = 256;
 constexpr int kStage = (kMaxBlockChunks + kGroupThreads - 1) / kGroupThreads;  // 12 chunks per producer thread per block at most
 constexpr int kEpiStride = 25;            // floats per staged row (24 values + 1: conflict-free row-per-lane writes)
 constexpr int kEpiFloats = 8 * 32 * kEpiStride;  // one [32 rows][25] transpose buffer per epilogue warp
-constexpr size_t kSmem = sizeof(float) * (kStages * kStageFloats + kBFloats + kEpiFloats) + 128;
+constexpr size_t kSmem = sizeof(float) * (kStages * kStageFloats + kRawStages * kAFloats + kBFloats + kEpiFloats) + 256;
 
 // rows per chunk column of an octave's blocks: 128 frames + window / hop - 1 shifts, rounded up to an odd
 // number (conflict-free transposed 16-byte stores)
@@ -104,6 +121,9 @@ struct CqtTcParams {
   int dec_tile_outputs;
   int debug;   // diagnostic bit mask (AST_CQT_DEBUG): 1 no epilogue stores, 2 no producer loads, 4 no MMAs, 8 no L2 prefetch
   OutSpec out;
+  int use_tma;                 // 1: blocks arrive through the tensor maps below; 0: register path (unaligned input rows)
+  int tma_end[kOctaves];       // samples of a clip's octave signal the map covers (whole rows of `hop` samples)
+  CUtensorMap maps[kOctaves];  // (sample in row < hop, row, clip) over each octave's signals, box = one block
 };
 
 // One producer thread's share of a block: chunk i (0..n-1) is read at s0 + i * src_step (samples) and stored at
@@ -116,6 +136,8 @@ struct BlockPlan {
   int n;
   bool vec_ok;
   bool interior;  // whole block inside [0, len) and 16-byte loads legal: no bounds checks
+                  // (TMA path: no sample at or past ok_end - rows before the clip arrive as zeros by themselves)
+  int ok_end;     // TMA path: min(len, samples the tensor map covers); chunks reaching past it are re-read from global
   bool coherent;  // octave >= 1: written by the decimator launch this kernel overlaps with -> loads go through L2
   const int* dep; // first completion counter this block waits for (nullptr: none), dep_n of them
   int dep_n;
@@ -165,10 +187,16 @@ __device__ __forceinline__ BlockPlan plan_block(const CqtTcParams& p, int b, int
   }
   s.n = tid < n_chunks ? (n_chunks - tid + kGroupThreads - 1) / kGroupThreads : 0;
   s.interior = first >= 0 && last <= s.len && s.vec_ok;
+  s.ok_end = s.len;
+  if (p.use_tma) {
+    s.ok_end = s.len < p.tma_end[oct] ? s.len : p.tma_end[oct];
+    s.interior = last <= s.ok_end;
+  }
   s.coherent = oct > 0;
   s.dep = nullptr;
   s.dep_n = 0;
-  if (oct > 0 && p.flags && !((stages_complete >> (oct - 1)) & 1)) {  // (a finished stage needs no bookkeeping)
+  if (oct > 0 && p.flags && !p.use_tma && !((stages_complete >> (oct - 1)) & 1)) {  // (a finished stage needs no bookkeeping;
+                                                                                   // TMA path: the TMA thread waits)
     // decimator stage oct - 1 produced samples [lo, hi) of this octave in tiles lo / 7424 ... (hi - 1) / 7424
     const int lo = first > 0 ? first : 0, hi = last < s.len ? last : s.len;
     if (hi > lo) {
@@ -221,20 +249,23 @@ __device__ __forceinline__ void issue_block(uint32_t a_hi_addr, uint32_t b_addr,
   }
 }
 
-__global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTcParams p) {
+__global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __grid_constant__ CqtTcParams p) {
   using namespace cqt_tc;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* a_stage = reinterpret_cast<float*>(smem_raw);            // [4 stages][hi | lo]
-  float* b_img = a_stage + kStages * kStageFloats;                // 64 KB
+  float* a_stage = reinterpret_cast<float*>(smem_raw);            // [kStages][hi | lo]
+  float* raw_stage = a_stage + kStages * kStageFloats;            // [kRawStages] blocks as TMA delivers them (row-major)
+  float* b_img = raw_stage + kRawStages * kAFloats;               // 64 KB
   float* epi_buf = b_img + kBFloats;                              // [8 warps][32][25] epilogue transpose
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + kEpiFloats);
   // stage s = block number % 4 always belongs to producer group s % 2, so every barrier is completed and waited in
   // strict phase order by one party on each side
-  uint64_t* full = bars;            // [4] producers -> MMA   (3 arrivals: the warps of one producer group)
-  uint64_t* empty = bars + 4;       // [4] MMA -> producers   (tcgen05.commit)
+  uint64_t* full = bars;            // [3] producers -> MMA   (3 arrivals: the warps of one producer group)
+  uint64_t* empty = bars + 4;       // [3] MMA -> producers   (tcgen05.commit)
   uint64_t* acc_full = bars + 8;    // [2] MMA -> epilogue    (tcgen05.commit)
   uint64_t* acc_empty = bars + 10;  // [2] epilogue -> MMA    (4 arrivals: one per epilogue warp)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* raw_full = bars + 12;   // [4] TMA -> splitters   (1 arrival + the box's bytes)
+  uint64_t* raw_empty = bars + 16;  // [4] splitters -> TMA   (3 arrivals: the warps of the group that owns the stage)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   pdl_launch_dependents();
@@ -250,6 +281,10 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
     for (int i = 0; i < 2; ++i) {
       umma::mbar_init(acc_full + i, 1);
       umma::mbar_init(acc_empty + i, 4);
+    }
+    for (int i = 0; i < kRawStages; ++i) {
+      umma::mbar_init(raw_full + i, 1);
+      umma::mbar_init(raw_empty + i, kGroupThreads / 32);
     }
   }
   umma::fence_proxy_async_smem();
@@ -341,7 +376,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
         j = 0;
         if (tile < total) decode_tile(p, tile, b, oct, t0);
         // one thread asks L2 for the signal span of the tile after that one, so its loads find it there
-        if (tid == 0 && tile + (int)gridDim.x < total && !(p.debug & 8)) {
+        if (tid == 0 && !p.use_tma && tile + (int)gridDim.x < total && !(p.debug & 8)) {
           int b2, oct2, t2;
           decode_tile(p, tile + gridDim.x, b2, oct2, t2);
           const long long len2 = ((p.lengths ? p.lengths[b2] : p.max_samples) + (1LL << oct2) - 1) >> oct2;
@@ -358,16 +393,59 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
       }
     };
     if (grp == 1 && tile < total) advance();   // group 1 starts at block 1
+    if (p.use_tma) {
+      // ------------------------------------------------------------- splitters (blocks arrive through TMA)
+      // raw stage `grp` holds the block row-major exactly as plan_block numbers its chunks: chunk u = tg + 96 i of the
+      // block is 16 bytes at raw + 16 u, whatever the octave.
+      static_assert(kRawStages % 2 == 0, "a raw stage belongs to one splitter group");
+      for (int item = grp; tile < total; item += 2) {
+        const int s = item % kStages, rs = item % kRawStages;
+        const float4* raw = reinterpret_cast<const float4*>(raw_stage + rs * kAFloats) + tg;
+        const BlockPlan sp = plan_block(p, b, oct, t0, j, tg, 0u);
+        if (warp == 0) AST_STAMP(0, item, 0);
+        umma::mbar_wait(raw_full + rs, (item / kRawStages) & 1);        // the box has landed
+        umma::mbar_wait(empty + s, ((item / kStages) & 1) ^ 1);        // the MMAs that read this operand stage are done
+        if (warp == 0) AST_STAMP(0, item, 2);
+        float4* a_hi = reinterpret_cast<float4*>(a_stage + s * kStageFloats);
+        float4* a_lo = a_hi + kAFloats / 4;
+#pragma unroll
+        for (int i = 0; i < kStage; ++i)
+          if (i < sp.n) {
+            float4 x4 = raw[kGroupThreads * i];
+            if (!sp.interior) {
+              // a chunk that reaches the clip's end (zero extension) or the end of what the tensor map covers (the last,
+              // partial row of hop samples of an octave-0 clip): re-read from global with the bounds applied
+              const int smp = sp.s0 + i * sp.src_step;
+              if (smp + 3 >= sp.ok_end)
+                x4 = sp.coherent ? umma::load4_zero_ext_cg(sp.x, smp, sp.len) : umma::load4_zero_ext(sp.x, smp, sp.len, sp.vec_ok);
+            }
+            float4 h, l;
+            umma::split_tf32(x4, h, l);
+            a_hi[sp.slot0 + i * sp.slot_step] = x4;   // raw: the tensor core truncates to TF32 itself (measured)
+            a_lo[sp.slot0 + i * sp.slot_step] = l;
+          }
+        if (warp == 0) AST_STAMP(0, item, 3);
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(raw_empty + rs);   // (the raw values are in registers / stored by now)
+        umma::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(full + s);
+        if (warp == 0) AST_STAMP(0, item, 4);
+        advance();
+        if (tile < total) advance();
+        if (warp == 0) AST_STAMP(0, item, 1);
+      }
+    } else {
     BlockPlan sp;
     if (tile < total) {
       sp = plan_block(p, b, oct, t0, j, tg, stages_complete);
       issue_loads(sp);
     }
     for (int item = grp; tile < total; item += 2) {
-      const int s = item & (kStages - 1);
+      const int s = item % kStages;
       if (warp == 0) AST_STAMP(0, item, 0);
-      // the MMAs that read this stage four blocks ago are done
-      umma::mbar_wait(empty + s, ((item >> 2) & 1) ^ 1);
+      // the MMAs that read this stage kStages blocks ago are done
+      umma::mbar_wait(empty + s, ((item / kStages) & 1) ^ 1);
       if (warp == 0) AST_STAMP(0, item, 2);
       float4* a_hi = reinterpret_cast<float4*>(a_stage + s * kStageFloats);
       float4* a_lo = a_hi + kAFloats / 4;
@@ -393,6 +471,83 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
       }
       if (warp == 0) AST_STAMP(0, item, 1);
     }
+    }
+  } else if (warp == kTmaWarp) {
+    // ================================================================= TMA (one thread)
+    if (p.use_tma && lane == 0) {
+      for (int i = 0; i < kOctaves; ++i) umma::prefetch_tensormap(&p.maps[i]);
+      unsigned stages_complete = 0;
+      int item = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int b, oct, t0;
+        decode_tile(p, tile, b, oct, t0);
+        const int hop = kHop >> oct;
+        const int n_blocks = blocks_per_tile(oct);
+        const int cols = (hop < 32 ? hop : 32);                      // floats per row of the box
+        const uint32_t bytes = (uint32_t)(block_rows(oct) * cols * 4);
+        const long long len0 = p.lengths ? p.lengths[b] : p.max_samples;
+        const int len = (int)((len0 + (1LL << oct) - 1) >> oct);
+        // one thread asks L2 for the signal span of the tile after next, so its box finds it there
+        if (tile + 2 * (int)gridDim.x < total && !(p.debug & 8)) {
+          int b2, oct2, t2;
+          decode_tile(p, tile + 2 * gridDim.x, b2, oct2, t2);
+          const long long len2 = ((p.lengths ? p.lengths[b2] : p.max_samples) + (1LL << oct2) - 1) >> oct2;
+          const float* x2 = oct2 == 0 ? p.wave + (long long)b2 * p.wave_stride
+                                      : p.ws + (long long)b2 * p.ws_clip_stride + p.oct_off[oct2];
+          const int hop2 = kHop >> oct2;
+          long long lo = (long long)t2 * hop2 - kCqtNfft / 2, hi = lo + (long long)(kM - 1) * hop2 + kCqtNfft;
+          if (lo < 0) lo = 0;
+          if (hi > len2) hi = len2;
+          const uintptr_t a0 = (reinterpret_cast<uintptr_t>(x2 + lo) + 15) & ~(uintptr_t)15;
+          const uintptr_t a1 = reinterpret_cast<uintptr_t>(x2 + hi) & ~(uintptr_t)15;
+          // (a span the decimator has not produced yet would only prefetch stale lines of the workspace: harmless,
+          // the box itself is issued after the counters below say the data is there)
+          if (a1 > a0) umma::prefetch_l2_bulk(reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0));
+        }
+        for (int j = 0; j < n_blocks; ++j, ++item) {
+          const int rs = item % kRawStages;
+          const int first = t0 * hop - kCqtNfft / 2 + 32 * j;
+          // the decimator tiles that produce the block's samples (octave >= 1), unless their whole stage is known done
+          if (oct > 0 && p.flags && !((stages_complete >> (oct - 1)) & 1)) {
+            int f;
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(p.stage_done + oct - 1) : "memory");
+            if (f >= p.stage_tiles[oct - 1]) {
+              __threadfence();
+              stages_complete |= 1u << (oct - 1);
+            } else {
+              const int last = first + (block_rows(oct) - 1) * hop + (hop < 32 ? hop : 32);
+              const int lo = first > 0 ? first : 0, hi = last < len ? last : len;
+              if (hi > lo) {
+                const int k_lo = lo / p.dec_tile_outputs, k_hi = (hi - 1) / p.dec_tile_outputs;
+                const int* dep = p.flags + ((long long)(oct - 1) * p.batch + b) * p.flag_tiles0;
+                unsigned long long t_first = 0;
+                for (uint32_t spin = 0;; ++spin) {
+                  int ok = 1;
+                  for (int k = k_lo; k <= k_hi; ++k) {
+                    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(dep + k) : "memory");
+                    ok &= f >= 4 ? 1 : 0;
+                  }
+                  if (ok) break;
+                  __nanosleep(200);
+                  if ((spin & 1023) == 1023) {
+                    const unsigned long long now = umma::global_ns();
+                    if (t_first == 0) t_first = now;
+                    if (now - t_first > umma::kPollTimeoutNs) __trap();
+                  }
+                }
+                __threadfence();   // acquire: the decimator's stores are visible to the loads issued from here on
+              }
+            }
+          }
+          umma::mbar_wait(raw_empty + rs, ((item / kRawStages) & 1) ^ 1);   // the splitters have drained this raw stage
+          umma::mbar_arrive_expect_tx(raw_full + rs, bytes);
+          // sample first + 4 e + R hop of the block = tensor element (col0 + 4 e, row0 + R): first = row0 hop + col0
+          const int q = 32 * j - kCqtNfft / 2;                      // first - t0 hop, in [-128, 128)
+          const int dr = q >= 0 ? q / hop : -((-q + hop - 1) / hop);   // floor(q / hop)
+          umma::tma_load_3d(raw_stage + rs * kAFloats, &p.maps[oct], raw_full + rs, q - dr * hop, t0 + dr, b);
+        }
+      }
+    }
   } else if (warp == kMmaWarp) {
     // ================================================================= MMA issue
     const uint32_t idesc64 = umma::instr_desc_tf32(kM, 2 * kN), idesc32 = umma::instr_desc_tf32(kM, kN);
@@ -406,9 +561,9 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
       umma::fence_after_thread_sync();
       const int n_blocks = oct == 0 ? 8 : oct == 1 ? 4 : oct == 2 ? 2 : 1;
       for (int j = 0; j < n_blocks; ++j, ++item) {
-        const int s = item & (kStages - 1);
+        const int s = item % kStages;
         AST_STAMP(1, item, 0);
-        umma::mbar_wait(full + s, (item >> 2) & 1);
+        umma::mbar_wait(full + s, (item / kStages) & 1);
         umma::fence_after_thread_sync();
         AST_STAMP(1, item, 1);
         if (umma::elect_one_sync()) {
@@ -534,8 +689,10 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const CqtTc
         stg[lane * kEpiStride + c] = v;
       }
       __syncwarp();
+      if (warp == kEpilogueWarp0) AST_STAMP(2, n_tile, 4);
       TileCtx nxt = ctx;
       if (tile + stride2 < total) nxt = load_ctx(tile + stride2);
+      if (warp == kEpilogueWarp0) AST_STAMP(2, n_tile, 5);
       if (stats_mode) {
         // compute_stats' per-clip reductions (compute_separated_stats.py:27-28) for this quadrant: lane c walks column
         // c of the staged 32 x 24 block (Welford over the live rows) and leaves (mean, M2); nothing else is stored
@@ -625,10 +782,61 @@ int cqt_tc_init() {
   return AST_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// Tensor maps over the seven octave signals of the batch: element (c, r, b) = sample r hop + c of clip b's octave
+// signal, i.e. rows of `hop` samples whose stride is the hop - consecutive rows are consecutive frames' window starts.
+// A box of (32 samples, rows of a block, 1 clip) is one staged block; coordinates may be negative (before the clip)
+// or past the last row: those elements arrive as zeros, which is librosa's zero padding (pad_mode = "constant").
+// Octave 0 lives in the caller's buffer: only WHOLE rows inside a clip are mapped (no read past the last clip's end);
+// the partial last row is re-read by the splitters (BlockPlan::ok_end).  Octaves >= 1 live in the workspace, whose
+// per-octave padding and following regions make a partial last row readable (its tail is masked by the clip length).
+static bool make_cqt_tensor_maps(CqtTcParams& p, const float* wave, long long wave_stride, const float* ws,
+                                 long long ws_clip_stride, int batch, long long max_samples) {
+  EncodeTiledFn encode = tensor_map_encoder();
+  if (!encode) return false;
+  if ((reinterpret_cast<uintptr_t>(wave) & 15) || (wave_stride % 4 != 0 && batch > 1) || (reinterpret_cast<uintptr_t>(ws) & 15) ||
+      ws_clip_stride % 4 != 0)
+    return false;
+  for (int oct = 0; oct < kOctaves; ++oct) {
+    const int hop = kHop >> oct;
+    const long long len = octave_len(max_samples, oct);
+    const long long rows = oct == 0 ? len / hop : (len + hop - 1) / hop;
+    if (rows < 1) return false;
+    const float* base = oct == 0 ? wave : ws + p.oct_off[oct];
+    const long long clip_stride = oct == 0 ? (batch > 1 ? wave_stride : max_samples + (4 - max_samples % 4) % 4) : ws_clip_stride;
+    if (reinterpret_cast<uintptr_t>(base) & 15) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)hop, (cuuint64_t)rows, (cuuint64_t)batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)hop * 4, (cuuint64_t)clip_stride * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)(hop < 32 ? hop : 32), (cuuint32_t)cqt_tc::block_rows(oct), 1};
+    const cuuint32_t elem[3] = {1, 1, 1};
+    if (encode(&p.maps[oct], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, elem,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+    p.tma_end[oct] = (int)(rows * hop);
+  }
+  return true;
+}
+
 int launch_cqt_tc(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
                   long long wave_stride, const float* ws, long long ws_clip_stride, const int* dec_flags, const OutSpec& out,
                   cudaStream_t st) {
   CqtTcParams p;
+  memset(&p, 0, sizeof(p));
   p.flags = dec_flags;
   p.flag_tiles0 = decimator_tiles_stage0(max_samples);
   p.stage_done = dec_flags ? dec_flags + decimator_stage_done_offset(batch, max_samples) : nullptr;
@@ -654,6 +862,11 @@ int launch_cqt_tc(const ast_plan* plan, const float* wave, const int32_t* length
   p.vec_ok = (wave_stride % 4 == 0 || batch == 1) && ((reinterpret_cast<uintptr_t>(wave) & 15) == 0);
   p.out = out;
   if (p.slots == 0 || batch == 0) return AST_OK;
+  {
+    const char* env = getenv("AST_CQT_TMA");   // diagnostic A/B switch: "0" keeps the register-staged producers
+    p.use_tma = (!env || strcmp(env, "0") != 0) && p.vec_ok &&
+                make_cqt_tensor_maps(p, wave, wave_stride, ws, ws_clip_stride, batch, max_samples) ? 1 : 0;
+  }
   if (2LL * p.slots * out.f_row * (out.layout == AST_LAYOUT_FLAT ? 1 : 2) >= (1LL << 31))
     return fail(AST_ERR_INVALID_ARG, "clip too long for the CQT epilogue's 32-bit in-clip offsets");
   long long ctas = (long long)p.tiles_per_clip_oct * kOctaves * batch;

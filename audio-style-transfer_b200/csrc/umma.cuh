@@ -49,6 +49,22 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// TMA: the calling thread arrives on the barrier and announces `bytes` of asynchronous writes that will complete it
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA tiled load of one 3-D box (coordinates innermost first; out-of-range elements arrive as zeros) into shared
+// memory; the barrier receives complete_tx for the whole box
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tensor_map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tensor_map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const void* tensor_map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tensor_map) : "memory");
+}
+
 // wall-clock nanoseconds (for the bounds of the cross-CTA polling loops: a count of polls would also trip under a
 // sanitizer or a debugger, where everything runs orders of magnitude slower)
 __device__ __forceinline__ unsigned long long global_ns() {

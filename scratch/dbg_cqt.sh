@@ -1,8 +1,6 @@
 #!/bin/bash
-# diagnostic: CQT kernel time with parts of the pipeline disabled (AST_CQT_DEBUG bit mask)
-for d in ${@:-0 1 2 4 3 5 6 7}; do
-  AST_CQT_DEBUG=$d python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('debug=$d', 'cqt', round(d['roofline']['kernels']['cqt_tc_kernel']['ms_per_step'],4), 'dec', round(d['roofline']['kernels']['decimate2_tc_kernel']['ms_per_step'],4), 'step', round(d['ms_per_step'],4))"
+# diagnostic: CQT kernel time with parts of the pipeline disabled (AST_CQT_DEBUG bit mask: 1 no epilogue stores,
+# 2 no producer loads (register path), 4 no MMAs, 8 no L2 prefetch)
+for d in ${@:-0 1 4 5 8}; do
+  echo -n "debug=$d "; AST_CQT_DEBUG=$d python scratch/prof_step.py --steps 20 --legs features --profile
 done

@@ -38,3 +38,13 @@ print("mean item period", d.mean(), "median", np.median(d))
 print("producer: issue loads", (P[:n_items,1]-P[:n_items,0]).mean(), "wait empty", (P[:n_items,2]-P[:n_items,1]).mean(),
       "split+store (incl load wait)", (P[:n_items,3]-P[:n_items,2]).mean(), "fence+arrive", (P[:n_items,4]-P[:n_items,3]).mean())
 print("mma: wait full", (M[:n_items,1]-M[:n_items,0]).mean(), "issue", (M[:n_items,2]-M[:n_items,1]).mean())
+# TMA path (splitters): stamps are 0 top, 2 waits done (box landed + operand stage free), 3 split + stored, 4 arrived, 1 advanced
+print("splitter (TMA path): wait raw/empty", (P[:n_items:2,2]-P[:n_items:2,0]).mean(), "split+store", (P[:n_items:2,3]-P[:n_items:2,2]).mean(),
+      "fence+arrive", (P[:n_items:2,4]-P[:n_items:2,3]).mean(), "advance", (P[:n_items:2,1]-P[:n_items:2,4]).mean(),
+      "| period of group 0 (2 blocks)", np.diff(P[:n_items:2,0]).mean())
+nt = int((buf[2, :, 0] > 0).sum())
+Ev = E[:nt][E[:nt, 0] > 0]
+print("epilogue group 0: wait acc", (Ev[:,1]-Ev[:,0]).mean(), "drain TMEM", (Ev[:,2]-Ev[:,1]).mean(), "scale+transpose+store", (Ev[:,3]-Ev[:,2]).mean(),
+      "| tile period (2 tiles)", np.diff(Ev[:,0]).mean())
+print("epilogue detail: scale+transpose", (Ev[:,4]-Ev[:,2]).mean(), "load_ctx(next)", (Ev[:,5]-Ev[:,4]).mean(), "store loop", (Ev[:,3]-Ev[:,5]).mean())
+print("total cycles CTA 0:", max(P[:n_items].max(), M[:n_items].max(), E[:nt].max()))
