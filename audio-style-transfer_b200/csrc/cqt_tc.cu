@@ -28,19 +28,24 @@
 //
 // One persistent CTA per SM, 16 warps:
 //   warp  6     TMA: one thread walks the CTA's block sequence; per block it waits for the decimator tiles the block
-//               reads (completion counters) and for a free raw stage, then issues ONE cp.async.bulk.tensor.3d - a box of
-//               (32 samples, 128..191 rows, 1 clip) out of a per-octave tensor map whose row stride is the octave's hop,
-//               so the box IS the block's chunk columns; rows before the clip (and past the map) arrive as zeros
-//   warps 0-5   splitters: raw stage (row-major, as TMA wrote it) -> hi / lo split -> chunk-column A block of the 3-stage
-//               operand ring.  Two groups of three warps take alternate blocks (group g owns raw stage g).  Round 1's
-//               producers fetched the samples themselves (LDG -> registers): a thread's fence.proxy.async and
-//               releasing mbarrier.arrive wait for its outstanding loads, which exposed ~ 34 us of load latency per
-//               64 clips; with the loads on the TMA engine the splitters touch shared memory only.  (Inputs whose
-//               rows are not 16-byte aligned cannot be described by a tensor map: they keep the register path.)
+//               reads (completion counters) and for a free stage, then issues one cp.async.bulk.tensor.3d PER CHUNK
+//               COLUMN - a box of (4 samples, 128..192 rows, 1 clip) out of a per-octave tensor map whose row stride
+//               is the octave's hop.  Rows 16 bytes apart are exactly the K-major no-swizzle operand layout, so the
+//               boxes land where the MMA reads them (the hi image: the tensor core truncates raw FP32 to TF32 itself);
+//               rows before the clip and past the map arrive as zeros (librosa's zero padding)
+//   warps 0-5   splitters: lo[u] = x[u] - trunc_tf32(x[u]) at the same offset of the stage's second half, an
+//               elementwise pass over shared memory (blocks that reach the clip's end re-read their tail chunks from
+//               global with the bounds applied and patch both images).  Round 1's producers fetched the samples
+//               themselves (LDG -> registers -> transposing stores): a thread's fence.proxy.async and releasing
+//               mbarrier.arrive wait for its outstanding loads, which exposed the load latency, and the per-block
+//               index algebra was the other half of their time.  (Inputs whose rows are not 16-byte aligned cannot be
+//               described by a tensor map: they keep that register path.)
+//   warp  7     MMA issue: one elected lane; the hi * [hi | lo] products of a block go out as soon as its boxes have
+//               landed, the lo * hi products when the splitters are done; tcgen05.commit releases stages and publishes
+//               accumulator sets
 //   warps 8-15  epilogue : TMEM -> registers -> shared transpose -> global; two groups of four warps (one TMEM lane
 //               quadrant each) take alternate tiles, i.e. one accumulator set each - the epilogue, not the tensor
 //               pipe, is the longest stage of a tile (scratch/trace_cqt.py, scratch/dbg_cqt.sh)
-//   warp  7     MMA issue: one elected lane, tcgen05.commit releases A stages and publishes accumulator sets
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -62,17 +67,9 @@ constexpr int kMmaWarp = 7;
 constexpr int kEpilogueWarp0 = 8;       // warps 8-11: even tiles, warps 12-15: odd tiles
 constexpr int kThreads = 16 * 32;       // 4 warps per scheduler: 128 registers per thread
 constexpr int kBlockCols = 8;                             // chunk columns per block (32 samples of every row)
-#ifndef AST_CQT_STAGES
-#define AST_CQT_STAGES 2
-#endif
-#ifndef AST_CQT_RAW_STAGES
-#define AST_CQT_RAW_STAGES 4
-#endif
-constexpr int kStages = AST_CQT_STAGES;                   // ring of staged operand blocks (hi + lo)
-constexpr int kRawStages = AST_CQT_RAW_STAGES;            // ring of raw blocks as TMA delivers them (two per splitter group:
-                                                          // the box of a group's next block is in flight while it splits one)
-constexpr int kMaxBlockChunks = 8 * 135;                  // octave 3: the largest block, 1080 chunks
-constexpr int kAFloats = kMaxBlockChunks * 4;             // 4320 floats = 17 280 B per split term
+constexpr int kStages = 4;                                // ring of staged blocks (hi + lo)
+constexpr int kMaxBlockChunks = 8 * 136;                  // octaves 0-3: the largest blocks, 1088 chunks
+constexpr int kAFloats = kMaxBlockChunks * 4;             // 4352 floats = 17 408 B per split term
 constexpr int kStageFloats = 2 * kAFloats;                // hi + lo
 constexpr int kBStepFloats = 2 * 2 * kN * 4;              // one K-step of [B_hi | B_lo]: [c 2][j 64][4] = 512 floats
 constexpr int kBFloats = kKSteps * kBStepFloats;          // 16384 floats = 64 KB
@@ -82,14 +79,15 @@ constexpr int kTmemCols = 256;
 constexpr int kStage = (kMaxBlockChunks + kGroupThreads - 1) / kGroupThreads;  // 12 chunks per producer thread per block at most
 constexpr int kEpiStride = 25;            // floats per staged row (24 values + 1: conflict-free row-per-lane writes)
 constexpr int kEpiFloats = 8 * 32 * kEpiStride;  // one [32 rows][25] transpose buffer per epilogue warp
-constexpr size_t kSmem = sizeof(float) * (kStages * kStageFloats + kRawStages * kAFloats + kBFloats + kEpiFloats) + 256;
+constexpr size_t kSmem = sizeof(float) * (kStages * kStageFloats + kBFloats + kEpiFloats) + 256 + 1024;   // + alignment slack
 
-// rows per chunk column of an octave's blocks: 128 frames + window / hop - 1 shifts, rounded up to an odd
-// number (conflict-free transposed 16-byte stores)
+// rows per chunk column of an octave's blocks: 128 frames + window / hop - 1 shifts, rounded up to a multiple of 8
+// (chunk columns are TMA destinations: 128-byte aligned)
 __host__ __device__ constexpr int block_rows(int oct) {
   return oct == 0 ? 128 : oct == 1 ? 129 : 127 + (256 >> (8 - oct));  // 128, 129, 131, 135, 143, 159, 191
 }
-__host__ __device__ constexpr int block_rt(int oct) { return block_rows(oct) | 1; }
+__host__ __device__ constexpr int block_rt(int oct) { return (block_rows(oct) + 7) & ~7; }  // 128, 136, 136, 136, 144, 160, 192
+__host__ __device__ constexpr int block_cols(int oct) { return oct <= 3 ? 8 : 8 >> (oct - 3); }  // chunk columns per block
 __host__ __device__ constexpr int blocks_per_tile(int oct) { return oct == 0 ? 8 : oct == 1 ? 4 : oct == 2 ? 2 : 1; }
 }  // namespace cqt_tc
 
@@ -213,24 +211,35 @@ __device__ __forceinline__ BlockPlan plan_block(const CqtTcParams& p, int b, int
 // A-descriptor offset is a compile-time constant.  K-step ks uses window chunks c' = 2 ks, 2 ks + 1.
 template <int OCT>
 __device__ __forceinline__ void issue_block(uint32_t a_hi_addr, uint32_t b_addr, uint32_t acc_set, int j,
-                                            uint32_t idesc64, uint32_t idesc32) {
+                                            uint32_t idesc64, uint32_t idesc32, int term_lo, int term_hi, bool sw128) {
   using namespace cqt_tc;
   constexpr int m = (kHop >> OCT) >> 2;
   constexpr int rt = block_rt(OCT);
   constexpr uint32_t lbo = m == 1 ? 16u : (uint32_t)rt * 16u;
   constexpr int n_steps = kKSteps / blocks_per_tile(OCT);  // 4, 8, 16 or 32 K-steps per block
-  const uint64_t da_hi0 = umma::smem_desc(a_hi_addr, lbo, 128);
-  const uint64_t da_lo0 = umma::smem_desc(a_hi_addr + kAFloats * 4, lbo, 128);
+  // TMA path, octaves 0-3: the block is ONE box of 128-byte rows in the SWIZZLE_128B layout; a window shift by d rows is
+  // + 128 d bytes on the start address, a K-step inside the row + 32 bytes.  The tensor core applies the swizzle to the
+  // ADDRESS bits (chunk bits 4..6 ^= row bits 7..9), so a start that is not 1024-byte aligned needs no base offset in the
+  // descriptor (measured on B200: base offset d mod 8 gives wrong rows, 0 matches the oracle to 1e-6).
+  // Octaves 4-6 (rows shorter than 128 bytes) and the register path: chunk columns, no swizzle.
+  const bool sw = sw128 && OCT <= 3;
+  const uint64_t da_hi0 = sw ? umma::smem_desc_sw128(a_hi_addr) : umma::smem_desc(a_hi_addr, lbo, 128);
+  const uint64_t da_lo0 = sw ? umma::smem_desc_sw128(a_hi_addr + kAFloats * 4) : umma::smem_desc(a_hi_addr + kAFloats * 4, lbo, 128);
   const uint64_t db0 = umma::smem_desc(b_addr, 2 * kN * 16, 128);
   // The products of one K-step go to accumulator ks & 1: first every hi * [hi | lo] of the block, then every
   // lo * hi, so that MMAs on the same TMEM columns stay several issues apart.
 #pragma unroll
   for (int term = 0; term < 2; ++term) {
+    if (term < term_lo || term > term_hi) continue;   // (TMA path: the hi terms go out before the lo image exists)
 #pragma unroll
     for (int i = 0; i < n_steps; ++i) {
       int ks_c;        // K-step for j == 0 (compile time); the block index adds 4 j (octaves 0..2)
       int a_units;     // A start-address offset in 16-byte units
-      if (OCT <= 2) {
+      if (sw) {
+        const int d = i >> 2, k = i & 3;            // row r + d of the box, K-step k of its 128 bytes
+        ks_c = (m / 2) * d + k;
+        a_units = 8 * d + 2 * k;
+      } else if (OCT <= 2) {
         const int d = i >> 2, k = i & 3;            // block j holds chunks m d + 8 j + e, e < 8, at row r + d
         ks_c = (m / 2) * d + k;
         a_units = 2 * k * rt + d;
@@ -249,23 +258,43 @@ __device__ __forceinline__ void issue_block(uint32_t a_hi_addr, uint32_t b_addr,
   }
 }
 
+// One out-of-line copy of the seven unrolled per-octave MMA sequences (every descriptor offset an immediate: ~4
+// instructions per MMA; a runtime loop over the same formulas cost ~280 cycles per MMA on the single issuing lane and
+// made the MMA warp the kernel's bottleneck).  Out of line because the kernel's roles share the SM's instruction caches:
+// inlined at both call sites of the TMA path (hi terms early, lo terms late) the sequences doubled, and a third of all
+// stall samples of that version were instruction fetches (ncu: stall_no_inst).
+__device__ __noinline__ void issue_block_any(int oct, uint32_t a_hi_addr, uint32_t b_addr, uint32_t acc_set, int j,
+                                             uint32_t idesc64, uint32_t idesc32, int term_lo, int term_hi, bool sw128) {
+  switch (oct) {
+    case 0: issue_block<0>(a_hi_addr, b_addr, acc_set, j, idesc64, idesc32, term_lo, term_hi, sw128); break;
+    case 1: issue_block<1>(a_hi_addr, b_addr, acc_set, j, idesc64, idesc32, term_lo, term_hi, sw128); break;
+    case 2: issue_block<2>(a_hi_addr, b_addr, acc_set, j, idesc64, idesc32, term_lo, term_hi, sw128); break;
+    case 3: issue_block<3>(a_hi_addr, b_addr, acc_set, j, idesc64, idesc32, term_lo, term_hi, sw128); break;
+    case 4: issue_block<4>(a_hi_addr, b_addr, acc_set, j, idesc64, idesc32, term_lo, term_hi, sw128); break;
+    case 5: issue_block<5>(a_hi_addr, b_addr, acc_set, j, idesc64, idesc32, term_lo, term_hi, sw128); break;
+    default: issue_block<6>(a_hi_addr, b_addr, acc_set, j, idesc64, idesc32, term_lo, term_hi, sw128); break;
+  }
+}
+
+template <bool kTma>
 __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __grid_constant__ CqtTcParams p) {
   using namespace cqt_tc;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* a_stage = reinterpret_cast<float*>(smem_raw);            // [kStages][hi | lo]
-  float* raw_stage = a_stage + kStages * kStageFloats;            // [kRawStages] blocks as TMA delivers them (row-major)
-  float* b_img = raw_stage + kRawStages * kAFloats;               // 64 KB
+  extern __shared__ __align__(128) unsigned char smem_dyn[];
+  // stages hold 128-byte-swizzled TMA boxes: 1024-byte aligned (the swizzle pattern repeats every 8 rows of 128 bytes)
+  unsigned char* smem_raw = smem_dyn + ((1024u - (umma::smem_u32(smem_dyn) & 1023u)) & 1023u);
+  float* a_stage = reinterpret_cast<float*>(smem_raw);            // [4 stages][hi | lo]
+  float* b_img = a_stage + kStages * kStageFloats;                // 64 KB
   float* epi_buf = b_img + kBFloats;                              // [8 warps][32][25] epilogue transpose
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + kEpiFloats);
   // stage s = block number % 4 always belongs to producer group s % 2, so every barrier is completed and waited in
   // strict phase order by one party on each side
-  uint64_t* full = bars;            // [3] producers -> MMA   (3 arrivals: the warps of one producer group)
-  uint64_t* empty = bars + 4;       // [3] MMA -> producers   (tcgen05.commit)
+  uint64_t* full = bars;            // [4] producers -> MMA   (TMA path: 6 arrivals, the splitter warps: lo image written;
+                                    //                         register path: 3 arrivals, the warps of one producer group)
+  uint64_t* empty = bars + 4;       // [4] MMA -> producers / TMA   (tcgen05.commit)
   uint64_t* acc_full = bars + 8;    // [2] MMA -> epilogue    (tcgen05.commit)
   uint64_t* acc_empty = bars + 10;  // [2] epilogue -> MMA    (4 arrivals: one per epilogue warp)
-  uint64_t* raw_full = bars + 12;   // [4] TMA -> splitters   (1 arrival + the box's bytes)
-  uint64_t* raw_empty = bars + 16;  // [4] splitters -> TMA   (3 arrivals: the warps of the group that owns the stage)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* hi_full = bars + 12;    // [4] TMA -> splitters + MMA   (1 arrival + the boxes' bytes: hi image landed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   pdl_launch_dependents();
@@ -275,16 +304,13 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
   if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, kTmemCols);
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
-      umma::mbar_init(full + i, kGroupThreads / 32);
+      umma::mbar_init(full + i, kTma ? kProducerWarps : kGroupThreads / 32);
       umma::mbar_init(empty + i, 1);
+      umma::mbar_init(hi_full + i, 1);
     }
     for (int i = 0; i < 2; ++i) {
       umma::mbar_init(acc_full + i, 1);
       umma::mbar_init(acc_empty + i, 4);
-    }
-    for (int i = 0; i < kRawStages; ++i) {
-      umma::mbar_init(raw_full + i, 1);
-      umma::mbar_init(raw_empty + i, kGroupThreads / 32);
     }
   }
   umma::fence_proxy_async_smem();
@@ -376,7 +402,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
         j = 0;
         if (tile < total) decode_tile(p, tile, b, oct, t0);
         // one thread asks L2 for the signal span of the tile after that one, so its loads find it there
-        if (tid == 0 && !p.use_tma && tile + (int)gridDim.x < total && !(p.debug & 8)) {
+        if (tid == 0 && !kTma && tile + (int)gridDim.x < total && !(p.debug & 8)) {
           int b2, oct2, t2;
           decode_tile(p, tile + gridDim.x, b2, oct2, t2);
           const long long len2 = ((p.lengths ? p.lengths[b2] : p.max_samples) + (1LL << oct2) - 1) >> oct2;
@@ -393,49 +419,61 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
       }
     };
     if (grp == 1 && tile < total) advance();   // group 1 starts at block 1
-    if (p.use_tma) {
+    if (kTma) {
       // ------------------------------------------------------------- splitters (blocks arrive through TMA)
-      // raw stage `grp` holds the block row-major exactly as plan_block numbers its chunks: chunk u = tg + 96 i of the
-      // block is 16 bytes at raw + 16 u, whatever the octave.
-      static_assert(kRawStages % 2 == 0, "a raw stage belongs to one splitter group");
-      for (int item = grp; tile < total; item += 2) {
-        const int s = item % kStages, rs = item % kRawStages;
-        const float4* raw = reinterpret_cast<const float4*>(raw_stage + rs * kAFloats) + tg;
-        const BlockPlan sp = plan_block(p, b, oct, t0, j, tg, 0u);
-        if (warp == 0) AST_STAMP(0, item, 0);
-        umma::mbar_wait(raw_full + rs, (item / kRawStages) & 1);        // the box has landed
-        umma::mbar_wait(empty + s, ((item / kStages) & 1) ^ 1);        // the MMAs that read this operand stage are done
-        if (warp == 0) AST_STAMP(0, item, 2);
-        float4* a_hi = reinterpret_cast<float4*>(a_stage + s * kStageFloats);
-        float4* a_lo = a_hi + kAFloats / 4;
-#pragma unroll
-        for (int i = 0; i < kStage; ++i)
-          if (i < sp.n) {
-            float4 x4 = raw[kGroupThreads * i];
-            if (!sp.interior) {
-              // a chunk that reaches the clip's end (zero extension) or the end of what the tensor map covers (the last,
-              // partial row of hop samples of an octave-0 clip): re-read from global with the bounds applied
-              const int smp = sp.s0 + i * sp.src_step;
-              if (smp + 3 >= sp.ok_end)
-                x4 = sp.coherent ? umma::load4_zero_ext_cg(sp.x, smp, sp.len) : umma::load4_zero_ext(sp.x, smp, sp.len, sp.vec_ok);
+      // The TMA thread has written the block's hi image in place (chunk-column operand layout).  All six warps make
+      // the lo image: lo[u] = x[u] - trunc_tf32(x[u]) at the SAME offset of the stage's second half - an elementwise
+      // pass, no index algebra.  Only a block that reaches the clip's end (or the end of what the tensor map covers)
+      // needs its tail chunks re-read with the bounds applied; those are patched in the hi image as well.
+      int item = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int b, oct, t0;
+        decode_tile(p, tile, b, oct, t0);
+        const int hop = kHop >> oct, rt = block_rt(oct), cols = block_cols(oct);
+        const int n_units = cols * rt;
+        const long long len0 = p.lengths ? p.lengths[b] : p.max_samples;
+        const int len = (int)((len0 + (1LL << oct) - 1) >> oct);
+        const int ok_end = len < p.tma_end[oct] ? len : p.tma_end[oct];
+        const float* x = oct == 0 ? p.wave + (long long)b * p.wave_stride : p.ws + (long long)b * p.ws_clip_stride + p.oct_off[oct];
+        for (int j = 0; j < blocks_per_tile(oct); ++j, ++item) {
+          const int s = item & (kStages - 1);
+          const int first = t0 * hop - kCqtNfft / 2 + 32 * j;
+          const bool interior = first + (rt - 1) * hop + 4 * cols <= ok_end;
+          float4* hi = reinterpret_cast<float4*>(a_stage + s * kStageFloats);
+          float4* lo = hi + kAFloats / 4;
+          if (warp == 0) AST_STAMP(0, item, 0);
+          umma::mbar_wait(hi_full + s, (item >> 2) & 1);   // the boxes have landed (and the stage's old MMAs are done)
+          if (warp == 0) AST_STAMP(0, item, 2);
+          if (interior) {
+            for (int u = tid; u < n_units; u += kProducerWarps * 32) {
+              const float4 x4 = hi[u];
+              float4 h, l;
+              umma::split_tf32(x4, h, l);
+              lo[u] = l;
             }
-            float4 h, l;
-            umma::split_tf32(x4, h, l);
-            a_hi[sp.slot0 + i * sp.slot_step] = x4;   // raw: the tensor core truncates to TF32 itself (measured)
-            a_lo[sp.slot0 + i * sp.slot_step] = l;
+          } else {
+            for (int u = tid; u < n_units; u += kProducerWarps * 32) {
+              float4 x4 = hi[u];
+              // octaves 0-3: 128-byte rows, chunk e of row r at position e ^ (r & 7); octaves 4-6: chunk columns
+              const int r = oct <= 3 ? u >> 3 : u % rt, e = oct <= 3 ? (u & 7) ^ (r & 7) : u / rt;
+              const int smp = first + r * hop + 4 * e;
+              if (smp + 3 >= ok_end) {
+                x4 = oct > 0 ? umma::load4_zero_ext_cg(x, smp, len) : umma::load4_zero_ext(x, smp, len, true);
+                hi[u] = x4;
+              }
+              float4 h, l;
+              umma::split_tf32(x4, h, l);
+              lo[u] = l;
+            }
           }
-        if (warp == 0) AST_STAMP(0, item, 3);
-        __syncwarp();
-        if (lane == 0) umma::mbar_arrive(raw_empty + rs);   // (the raw values are in registers / stored by now)
-        umma::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) umma::mbar_arrive(full + s);
-        if (warp == 0) AST_STAMP(0, item, 4);
-        advance();
-        if (tile < total) advance();
-        if (warp == 0) AST_STAMP(0, item, 1);
+          if (warp == 0) AST_STAMP(0, item, 3);
+          umma::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) umma::mbar_arrive(full + s);
+          if (warp == 0) AST_STAMP(0, item, 4);
+        }
       }
-    } else {
+    } else if (!kTma) {
     BlockPlan sp;
     if (tile < total) {
       sp = plan_block(p, b, oct, t0, j, tg, stages_complete);
@@ -474,7 +512,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
     }
   } else if (warp == kTmaWarp) {
     // ================================================================= TMA (one thread)
-    if (p.use_tma && lane == 0) {
+    if (kTma && lane == 0) {
       for (int i = 0; i < kOctaves; ++i) umma::prefetch_tensormap(&p.maps[i]);
       unsigned stages_complete = 0;
       int item = 0;
@@ -483,8 +521,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
         decode_tile(p, tile, b, oct, t0);
         const int hop = kHop >> oct;
         const int n_blocks = blocks_per_tile(oct);
-        const int cols = (hop < 32 ? hop : 32);                      // floats per row of the box
-        const uint32_t bytes = (uint32_t)(block_rows(oct) * cols * 4);
+        const int cols = block_cols(oct), rt = block_rt(oct);
         const long long len0 = p.lengths ? p.lengths[b] : p.max_samples;
         const int len = (int)((len0 + (1LL << oct) - 1) >> oct);
         // one thread asks L2 for the signal span of the tile after next, so its box finds it there
@@ -505,7 +542,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
           if (a1 > a0) umma::prefetch_l2_bulk(reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0));
         }
         for (int j = 0; j < n_blocks; ++j, ++item) {
-          const int rs = item % kRawStages;
+          const int s = item & (kStages - 1);
           const int first = t0 * hop - kCqtNfft / 2 + 32 * j;
           // the decimator tiles that produce the block's samples (octave >= 1), unless their whole stage is known done
           if (oct > 0 && p.flags && !((stages_complete >> (oct - 1)) & 1)) {
@@ -515,7 +552,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
               __threadfence();
               stages_complete |= 1u << (oct - 1);
             } else {
-              const int last = first + (block_rows(oct) - 1) * hop + (hop < 32 ? hop : 32);
+              const int last = first + (rt - 1) * hop + 4 * cols;
               const int lo = first > 0 ? first : 0, hi = last < len ? last : len;
               if (hi > lo) {
                 const int k_lo = lo / p.dec_tile_outputs, k_hi = (hi - 1) / p.dec_tile_outputs;
@@ -539,12 +576,21 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
               }
             }
           }
-          umma::mbar_wait(raw_empty + rs, ((item / kRawStages) & 1) ^ 1);   // the splitters have drained this raw stage
-          umma::mbar_arrive_expect_tx(raw_full + rs, bytes);
-          // sample first + 4 e + R hop of the block = tensor element (col0 + 4 e, row0 + R): first = row0 hop + col0
-          const int q = 32 * j - kCqtNfft / 2;                      // first - t0 hop, in [-128, 128)
+          umma::mbar_wait(empty + s, ((item >> 2) & 1) ^ 1);   // the MMAs that read this stage four blocks ago are done
+          umma::mbar_arrive_expect_tx(hi_full + s, (uint32_t)(cols * rt * 16));
+          // octaves 4-6: chunk column e of the block = samples first + 4 e + R hop, R < rt: a box of (4 samples, rt rows,
+          // 1 clip) at tensor element (col0 + 4 e, row0), first = row0 hop + col0 - rows 16 bytes apart in shared memory
+          // are exactly the K-major, no-swizzle operand layout, so the box lands where the MMA reads it
+          const int q = 32 * j - kCqtNfft / 2;                         // first - t0 hop, in [-128, 128)
           const int dr = q >= 0 ? q / hop : -((-q + hop - 1) / hop);   // floor(q / hop)
-          umma::tma_load_3d(raw_stage + rs * kAFloats, &p.maps[oct], raw_full + rs, q - dr * hop, t0 + dr, b);
+          float* dst = a_stage + s * kStageFloats;
+          if (oct <= 3) {
+            // rows of >= 128 bytes: ONE box of (32 samples, rt rows, 1 clip), 128-byte swizzled as the MMA expects it
+            umma::tma_load_3d(dst, &p.maps[oct], hi_full + s, q - dr * hop, t0 + dr, b);
+          } else {
+            for (int e = 0; e < cols; ++e)
+              umma::tma_load_3d(dst + e * rt * 4, &p.maps[oct], hi_full + s, q - dr * hop + 4 * e, t0 + dr, b);
+          }
         }
       }
     }
@@ -560,24 +606,32 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
       umma::mbar_wait(acc_empty + q, ((n_tile >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator set
       umma::fence_after_thread_sync();
       const int n_blocks = oct == 0 ? 8 : oct == 1 ? 4 : oct == 2 ? 2 : 1;
+      const int hop = kHop >> oct, rt = block_rt(oct), cols = block_cols(oct);
+      const long long len0 = p.lengths ? p.lengths[b] : p.max_samples;
+      const int len = (int)((len0 + (1LL << oct) - 1) >> oct);
+      const int ok_end = len < p.tma_end[oct] ? len : p.tma_end[oct];
       for (int j = 0; j < n_blocks; ++j, ++item) {
         const int s = item % kStages;
+        // TMA path: the hi * [hi | lo] products need only the boxes (hi image), unless the splitters have to patch the
+        // block's tail (clip end); the lo * hi products wait for the lo image.  Register path: one pass.
+        const bool early = kTma && t0 * hop - kCqtNfft / 2 + 32 * j + (rt - 1) * hop + 4 * cols <= ok_end;
+        const uint32_t a_hi_addr = umma::smem_u32(a_stage + s * kStageFloats);
+        const uint32_t acc_set = tmem_base + (uint32_t)(q * kSetCols);
+        auto issue = [&](int term_lo, int term_hi) {
+          if (!(p.debug & 4)) issue_block_any(oct, a_hi_addr, b_addr, acc_set, j, idesc64, idesc32, term_lo, term_hi, kTma);
+        };
         AST_STAMP(1, item, 0);
+        if (early) {
+          umma::mbar_wait(hi_full + s, (item / kStages) & 1);
+          umma::fence_after_thread_sync();
+          if (umma::elect_one_sync()) issue(0, 0);
+          __syncwarp();
+        }
         umma::mbar_wait(full + s, (item / kStages) & 1);
         umma::fence_after_thread_sync();
         AST_STAMP(1, item, 1);
         if (umma::elect_one_sync()) {
-          const uint32_t a_hi_addr = umma::smem_u32(a_stage + s * kStageFloats);
-          const uint32_t acc_set = tmem_base + (uint32_t)(q * kSetCols);
-          if (!(p.debug & 4)) switch (oct) {
-            case 0: issue_block<0>(a_hi_addr, b_addr, acc_set, j, idesc64, idesc32); break;
-            case 1: issue_block<1>(a_hi_addr, b_addr, acc_set, j, idesc64, idesc32); break;
-            case 2: issue_block<2>(a_hi_addr, b_addr, acc_set, j, idesc64, idesc32); break;
-            case 3: issue_block<3>(a_hi_addr, b_addr, acc_set, j, idesc64, idesc32); break;
-            case 4: issue_block<4>(a_hi_addr, b_addr, acc_set, j, idesc64, idesc32); break;
-            case 5: issue_block<5>(a_hi_addr, b_addr, acc_set, j, idesc64, idesc32); break;
-            default: issue_block<6>(a_hi_addr, b_addr, acc_set, j, idesc64, idesc32); break;
-          }
+          issue(early ? 1 : 0, 1);
           umma::commit(empty + s);                          // stage s may be overwritten once these MMAs finish
           if (j == n_blocks - 1) umma::commit(acc_full + q);    // ... and the accumulator set is complete
         }
@@ -641,10 +695,19 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
       return c;
     };
     const int stride2 = 2 * (int)gridDim.x;
-    int tile = blockIdx.x + group * (int)gridDim.x;
-    TileCtx ctx;
-    if (tile < total) ctx = load_ctx(tile);
-    for (int k = 0; tile < total; tile += stride2, ++k) {
+    // Rotation with ONE load_ctx site (code size: the epilogue's loop is the kernel's largest): an iteration first loads
+    // the context of the tile AFTER the one it is about to drain - before it waits for that tile's accumulators, so the
+    // context's global loads overlap the wait - then processes the current tile.
+    TileCtx ctx, nxt;
+    ctx.flags = 0;
+    for (int k = -1, tile = blockIdx.x + group * (int)gridDim.x - stride2;; tile += stride2, ++k) {
+      const bool has_next = tile + stride2 < total;
+      if (has_next) nxt = load_ctx(tile + stride2);
+      if (k < 0) {
+        if (!has_next) break;
+        ctx = nxt;
+        continue;
+      }
       const int n_tile = 2 * k + group;
       if (warp == kEpilogueWarp0) AST_STAMP(2, n_tile, 0);
       umma::mbar_wait(acc_full + group, k & 1);
@@ -690,8 +753,6 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
       }
       __syncwarp();
       if (warp == kEpilogueWarp0) AST_STAMP(2, n_tile, 4);
-      TileCtx nxt = ctx;
-      if (tile + stride2 < total) nxt = load_ctx(tile + stride2);
       if (warp == kEpilogueWarp0) AST_STAMP(2, n_tile, 5);
       if (stats_mode) {
         // compute_stats' per-clip reductions (compute_separated_stats.py:27-28) for this quadrant: lane c walks column
@@ -706,12 +767,13 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
           p.out.cqt_part[ctx.part_idx + lane] = make_float2(mean, m2);
         }
         __syncwarp();
+        if (!has_next) break;
         ctx = nxt;
         continue;
       }
       // 32 rows x 12 columns per plane = 12 store rounds; lane l of round i owns element 32 i + l
       float* const clip_out = ctx.clip_out;
-#pragma unroll
+#pragma unroll 3
       for (int i = 0; i < kBinsPerOctave; ++i) {
         const int idx = lane + 32 * i;
         const int r = idx / kBinsPerOctave, j = idx - r * kBinsPerOctave;
@@ -730,6 +792,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
       }
       __syncwarp();  // the staging buffer is rewritten by the next tile
       if (warp == kEpilogueWarp0) AST_STAMP(2, n_tile, 3);
+      if (!has_next) break;
       ctx = nxt;
     }
   }
@@ -778,7 +841,8 @@ extern "C" int ast_debug_cqt_trace(long long* host) {
 #endif
 
 int cqt_tc_init() {
-  AST_CUDA_TRY(cudaFuncSetAttribute(cqt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cqt_tc::kSmem));
+  AST_CUDA_TRY(cudaFuncSetAttribute(cqt_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cqt_tc::kSmem));
+  AST_CUDA_TRY(cudaFuncSetAttribute(cqt_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cqt_tc::kSmem));
   return AST_OK;
 }
 
@@ -799,8 +863,9 @@ static EncodeTiledFn tensor_map_encoder() {
 
 // Tensor maps over the seven octave signals of the batch: element (c, r, b) = sample r hop + c of clip b's octave
 // signal, i.e. rows of `hop` samples whose stride is the hop - consecutive rows are consecutive frames' window starts.
-// A box of (32 samples, rows of a block, 1 clip) is one staged block; coordinates may be negative (before the clip)
-// or past the last row: those elements arrive as zeros, which is librosa's zero padding (pad_mode = "constant").
+// A box of (4 samples, rows of a block, 1 clip) is one chunk column of a staged block, delivered straight in the MMA's
+// K-major no-swizzle operand layout (rows 16 bytes apart); coordinates may be negative (before the clip) or past the
+// last row: those elements arrive as zeros, which is librosa's zero padding (pad_mode = "constant").
 // Octave 0 lives in the caller's buffer: only WHOLE rows inside a clip are mapped (no read past the last clip's end);
 // the partial last row is re-read by the splitters (BlockPlan::ok_end).  Octaves >= 1 live in the workspace, whose
 // per-octave padding and following regions make a partial last row readable (its tail is masked by the clip length).
@@ -821,10 +886,13 @@ static bool make_cqt_tensor_maps(CqtTcParams& p, const float* wave, long long wa
     if (reinterpret_cast<uintptr_t>(base) & 15) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)hop, (cuuint64_t)rows, (cuuint64_t)batch};
     const cuuint64_t strides[2] = {(cuuint64_t)hop * 4, (cuuint64_t)clip_stride * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)(hop < 32 ? hop : 32), (cuuint32_t)cqt_tc::block_rows(oct), 1};
+    // octaves 0-3: the whole block, 32 samples = 128 bytes of rt consecutive rows, 128-byte swizzled;
+    // octaves 4-6: one chunk column, 16 bytes of rt consecutive rows
+    const cuuint32_t box[3] = {(cuuint32_t)(oct <= 3 ? 32 : 4), (cuuint32_t)cqt_tc::block_rt(oct), 1};
     const cuuint32_t elem[3] = {1, 1, 1};
     if (encode(&p.maps[oct], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, elem,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, oct <= 3 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return false;
     p.tma_end[oct] = (int)(rows * hop);
@@ -872,7 +940,10 @@ int launch_cqt_tc(const ast_plan* plan, const float* wave, const int32_t* length
   long long ctas = (long long)p.tiles_per_clip_oct * kOctaves * batch;
   if (ctas > plan->sm_count) ctas = plan->sm_count;  // persistent: one CTA per SM
   ProfileSpan span("cqt_tc_kernel", st);
-  AST_CUDA_TRY(launch_with_pdl(cqt_tc_kernel, dim3((unsigned)ctas), cqt_tc::kThreads, cqt_tc::kSmem, st, p));
+  if (p.use_tma)
+    AST_CUDA_TRY(launch_with_pdl(cqt_tc_kernel<true>, dim3((unsigned)ctas), cqt_tc::kThreads, cqt_tc::kSmem, st, p));
+  else
+    AST_CUDA_TRY(launch_with_pdl(cqt_tc_kernel<false>, dim3((unsigned)ctas), cqt_tc::kThreads, cqt_tc::kSmem, st, p));
   return AST_OK;
 }
 

@@ -18,6 +18,15 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_b
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);  // version = 1 (sm_100)
 }
 
+// K-major, SWIZZLE_128B canonical layout ((8, n), (4, 2)) : ((128 B, SBO), (4 B, 16 B)): rows of 128 bytes (four K-steps
+// of 8 TF32 values) whose 16-byte chunks are XOR-swizzled with the row index mod 8, 8-row groups SBO = 1024 B apart -
+// what a TMA box with CU_TENSOR_MAP_SWIZZLE_128B writes into a 1024-byte aligned buffer.  The K-step is selected by
+// + 32 B on the start address, a shift by whole rows by + 128 B per row: the swizzle is a function of the address bits,
+// so the descriptor's base offset stays 0 (measured).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
 // kind::tf32, FP32 accumulate, both operands K-major, no negate / sparsity
 __host__ __device__ constexpr uint32_t instr_desc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
