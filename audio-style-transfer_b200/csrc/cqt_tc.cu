@@ -64,8 +64,22 @@ constexpr int kGroupThreads = 96;       // producer group: three warps (a multip
 constexpr int kProducerWarps = 6;       // two groups, warps 0-2 and 3-5, alternate blocks
 constexpr int kTmaWarp = 6;             // one thread: tensor-map loads into the raw ring
 constexpr int kMmaWarp = 7;
-constexpr int kEpilogueWarp0 = 8;       // warps 8-11: even tiles, warps 12-15: odd tiles
-constexpr int kThreads = 16 * 32;       // 4 warps per scheduler: 128 registers per thread
+constexpr int kEpilogueWarp0 = 8;       // register path: warps 8-11 even tiles, warps 12-15 odd tiles; TMA path: warps 8-11
+constexpr int kThreads = 16 * 32;       // register path: 4 warps per scheduler, 128 registers per thread
+// AST_CQT_LEAN (diagnostic): the TMA-path kernel with 12 warps (one epilogue group), 3 operand stages and <= 120
+// registers, so that ONE 4-warp STFT CTA (34.8 KB, 16 K registers) fits next to it on every SM.  Measured on B200: it
+// works (the STFT's first CTAs start under the projection), but the step gets SLOWER (0.298 -> 0.317 ms per 64 clips):
+// this kernel is bound by shared-memory operand traffic and the instruction caches, which the STFT's warps also load,
+// and the programmatic chain's tail overlap (21 us) shrinks to 8 us.  Kept off.
+#ifdef AST_CQT_LEAN
+constexpr int kThreadsTma = 12 * 32;
+constexpr int kStagesTma = 3;
+constexpr int kEpiGroupsTma = 1;
+#else
+constexpr int kThreadsTma = kThreads;
+constexpr int kStagesTma = 4;
+constexpr int kEpiGroupsTma = 2;
+#endif
 constexpr int kBlockCols = 8;                             // chunk columns per block (32 samples of every row)
 constexpr int kStages = 4;                                // ring of staged blocks (hi + lo)
 constexpr int kMaxBlockChunks = 8 * 136;                  // octaves 0-3: the largest blocks, 1088 chunks
@@ -80,6 +94,7 @@ constexpr int kStage = (kMaxBlockChunks + kGroupThreads - 1) / kGroupThreads;  /
 constexpr int kEpiStride = 25;            // floats per staged row (24 values + 1: conflict-free row-per-lane writes)
 constexpr int kEpiFloats = 8 * 32 * kEpiStride;  // one [32 rows][25] transpose buffer per epilogue warp
 constexpr size_t kSmem = sizeof(float) * (kStages * kStageFloats + kBFloats + kEpiFloats) + 256 + 1024;   // + alignment slack
+constexpr size_t kSmemTma = sizeof(float) * (kStagesTma * kStageFloats + kBFloats + kEpiFloats / 2 * kEpiGroupsTma) + 256 + 1024;
 
 // rows per chunk column of an octave's blocks: 128 frames + window / hop - 1 shifts, rounded up to a multiple of 8
 // (chunk columns are TMA destinations: 128-byte aligned)
@@ -277,15 +292,18 @@ __device__ __noinline__ void issue_block_any(int oct, uint32_t a_hi_addr, uint32
 }
 
 template <bool kTma>
-__global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __grid_constant__ CqtTcParams p) {
+__global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads, 1)
+    cqt_tc_kernel(const __grid_constant__ CqtTcParams p) {
   using namespace cqt_tc;
+  constexpr int kNStages = kTma ? kStagesTma : kStages;   // operand stages of this variant
+  constexpr int kEpiGroups = kTma ? kEpiGroupsTma : 2;
   extern __shared__ __align__(128) unsigned char smem_dyn[];
   // stages hold 128-byte-swizzled TMA boxes: 1024-byte aligned (the swizzle pattern repeats every 8 rows of 128 bytes)
   unsigned char* smem_raw = smem_dyn + ((1024u - (umma::smem_u32(smem_dyn) & 1023u)) & 1023u);
   float* a_stage = reinterpret_cast<float*>(smem_raw);            // [4 stages][hi | lo]
-  float* b_img = a_stage + kStages * kStageFloats;                // 64 KB
+  float* b_img = a_stage + kNStages * kStageFloats;               // 64 KB
   float* epi_buf = b_img + kBFloats;                              // [8 warps][32][25] epilogue transpose
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + kEpiFloats);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + kEpiFloats / 2 * kEpiGroups);
   // stage s = block number % 4 always belongs to producer group s % 2, so every barrier is completed and waited in
   // strict phase order by one party on each side
   uint64_t* full = bars;            // [4] producers -> MMA   (TMA path: 6 arrivals, the splitter warps: lo image written;
@@ -299,11 +317,11 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
 
   pdl_launch_dependents();
   // B images: resident for the CTA's lifetime
-  for (int i = tid; i < kBFloats / 4; i += kThreads)
+  for (int i = tid; i < kBFloats / 4; i += (int)blockDim.x)
     reinterpret_cast<float4*>(b_img)[i] = __ldg(reinterpret_cast<const float4*>(p.bmat) + i);
   if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, kTmemCols);
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kNStages; ++i) {
       umma::mbar_init(full + i, kTma ? kProducerWarps : kGroupThreads / 32);
       umma::mbar_init(empty + i, 1);
       umma::mbar_init(hi_full + i, 1);
@@ -436,13 +454,13 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
         const int ok_end = len < p.tma_end[oct] ? len : p.tma_end[oct];
         const float* x = oct == 0 ? p.wave + (long long)b * p.wave_stride : p.ws + (long long)b * p.ws_clip_stride + p.oct_off[oct];
         for (int j = 0; j < blocks_per_tile(oct); ++j, ++item) {
-          const int s = item & (kStages - 1);
+          const int s = item % kNStages;
           const int first = t0 * hop - kCqtNfft / 2 + 32 * j;
           const bool interior = first + (rt - 1) * hop + 4 * cols <= ok_end;
           float4* hi = reinterpret_cast<float4*>(a_stage + s * kStageFloats);
           float4* lo = hi + kAFloats / 4;
           if (warp == 0) AST_STAMP(0, item, 0);
-          umma::mbar_wait(hi_full + s, (item >> 2) & 1);   // the boxes have landed (and the stage's old MMAs are done)
+          umma::mbar_wait(hi_full + s, (item / kNStages) & 1);   // the boxes have landed (and the stage's old MMAs are done)
           if (warp == 0) AST_STAMP(0, item, 2);
           if (interior) {
             for (int u = tid; u < n_units; u += kProducerWarps * 32) {
@@ -542,7 +560,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
           if (a1 > a0) umma::prefetch_l2_bulk(reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0));
         }
         for (int j = 0; j < n_blocks; ++j, ++item) {
-          const int s = item & (kStages - 1);
+          const int s = item % kNStages;
           const int first = t0 * hop - kCqtNfft / 2 + 32 * j;
           // the decimator tiles that produce the block's samples (octave >= 1), unless their whole stage is known done
           if (oct > 0 && p.flags && !((stages_complete >> (oct - 1)) & 1)) {
@@ -576,7 +594,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
               }
             }
           }
-          umma::mbar_wait(empty + s, ((item >> 2) & 1) ^ 1);   // the MMAs that read this stage four blocks ago are done
+          umma::mbar_wait(empty + s, ((item / kNStages) & 1) ^ 1);   // the MMAs that last read this stage are done
           umma::mbar_arrive_expect_tx(hi_full + s, (uint32_t)(cols * rt * 16));
           // octaves 4-6: chunk column e of the block = samples first + 4 e + R hop, R < rt: a box of (4 samples, rt rows,
           // 1 clip) at tensor element (col0 + 4 e, row0), first = row0 hop + col0 - rows 16 bytes apart in shared memory
@@ -611,7 +629,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
       const int len = (int)((len0 + (1LL << oct) - 1) >> oct);
       const int ok_end = len < p.tma_end[oct] ? len : p.tma_end[oct];
       for (int j = 0; j < n_blocks; ++j, ++item) {
-        const int s = item % kStages;
+        const int s = item % kNStages;
         // TMA path: the hi * [hi | lo] products need only the boxes (hi image), unless the splitters have to patch the
         // block's tail (clip end); the lo * hi products wait for the lo image.  Register path: one pass.
         const bool early = kTma && t0 * hop - kCqtNfft / 2 + 32 * j + (rt - 1) * hop + 4 * cols <= ok_end;
@@ -622,12 +640,12 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
         };
         AST_STAMP(1, item, 0);
         if (early) {
-          umma::mbar_wait(hi_full + s, (item / kStages) & 1);
+          umma::mbar_wait(hi_full + s, (item / kNStages) & 1);
           umma::fence_after_thread_sync();
           if (umma::elect_one_sync()) issue(0, 0);
           __syncwarp();
         }
-        umma::mbar_wait(full + s, (item / kStages) & 1);
+        umma::mbar_wait(full + s, (item / kNStages) & 1);
         umma::fence_after_thread_sync();
         AST_STAMP(1, item, 1);
         if (umma::elect_one_sync()) {
@@ -644,7 +662,9 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
     // TMEM holds one frame per lane; written that way every store instruction would touch 32 output rows
     // (32 L1 wavefronts for 128 B).  The 32 x 24 block is therefore transposed through shared memory and
     // stored with consecutive lanes on consecutive columns of a row (12-float runs, ~3 rows per instruction).
-    const int group = (warp - kEpilogueWarp0) >> 2;  // tiles n_tile = 2 k + group, accumulator set `group`
+    // register path: two groups, group g takes tiles n_tile = 2 k + g and accumulator set g;
+    // TMA path: one group takes every tile, accumulator sets alternate
+    const int group = (warp - kEpilogueWarp0) >> 2;
     const int quad = warp & 3;                       // the TMEM lane quadrant this warp may read
     float* stg = epi_buf + (warp - kEpilogueWarp0) * 32 * kEpiStride;
     const long long clip_floats = p.out.layout == AST_LAYOUT_FLAT ? 2LL * p.out.dim1 * p.out.f_row
@@ -694,7 +714,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
       }
       return c;
     };
-    const int stride2 = 2 * (int)gridDim.x;
+    const int stride2 = kEpiGroups * (int)gridDim.x;
     // Rotation with ONE load_ctx site (code size: the epilogue's loop is the kernel's largest): an iteration first loads
     // the context of the tile AFTER the one it is about to drain - before it waits for that tile's accumulators, so the
     // context's global loads overlap the wait - then processes the current tile.
@@ -708,14 +728,15 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
         ctx = nxt;
         continue;
       }
-      const int n_tile = 2 * k + group;
+      const int n_tile = kEpiGroups * k + group;
+      const int set = n_tile & 1;   // accumulator set of this tile
       if (warp == kEpilogueWarp0) AST_STAMP(2, n_tile, 0);
-      umma::mbar_wait(acc_full + group, k & 1);
+      umma::mbar_wait(acc_full + set, (n_tile >> 1) & 1);
       umma::fence_after_thread_sync();
       if (warp == kEpilogueWarp0) AST_STAMP(2, n_tile, 1);
       // 24 of each accumulator's 32 columns carry data: one x16 and one x8 load per part
       float acc[kCqtCols];
-      const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(group * kSetCols);
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(set * kSetCols);
       {
         float a16[16], a8[8];
         umma::tmem_ld_32x16(lane_base, a16);               // hi * hi, even K-steps
@@ -738,7 +759,7 @@ __global__ void __launch_bounds__(cqt_tc::kThreads, 1) cqt_tc_kernel(const __gri
       }
       umma::fence_before_thread_sync();
       __syncwarp();
-      if (lane == 0) umma::mbar_arrive(acc_empty + group);  // this warp's quadrant of the set is drained
+      if (lane == 0) umma::mbar_arrive(acc_empty + set);  // this warp's quadrant of the set is drained
       if (warp == kEpilogueWarp0) AST_STAMP(2, n_tile, 2);
 
       // scale + normalise (column constants broadcast from their lane), row-per-lane into the staging buffer
@@ -841,7 +862,7 @@ extern "C" int ast_debug_cqt_trace(long long* host) {
 #endif
 
 int cqt_tc_init() {
-  AST_CUDA_TRY(cudaFuncSetAttribute(cqt_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cqt_tc::kSmem));
+  AST_CUDA_TRY(cudaFuncSetAttribute(cqt_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cqt_tc::kSmemTma));
   AST_CUDA_TRY(cudaFuncSetAttribute(cqt_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cqt_tc::kSmem));
   return AST_OK;
 }
@@ -941,7 +962,7 @@ int launch_cqt_tc(const ast_plan* plan, const float* wave, const int32_t* length
   if (ctas > plan->sm_count) ctas = plan->sm_count;  // persistent: one CTA per SM
   ProfileSpan span("cqt_tc_kernel", st);
   if (p.use_tma)
-    AST_CUDA_TRY(launch_with_pdl(cqt_tc_kernel<true>, dim3((unsigned)ctas), cqt_tc::kThreads, cqt_tc::kSmem, st, p));
+    AST_CUDA_TRY(launch_with_pdl(cqt_tc_kernel<true>, dim3((unsigned)ctas), cqt_tc::kThreadsTma, cqt_tc::kSmemTma, st, p));
   else
     AST_CUDA_TRY(launch_with_pdl(cqt_tc_kernel<false>, dim3((unsigned)ctas), cqt_tc::kThreads, cqt_tc::kSmem, st, p));
   return AST_OK;
