@@ -12,6 +12,7 @@ import bench  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--legs", default="features,istft")
+ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--profile", action="store_true", help="per-kernel events (serialised launches)")
 a = ap.parse_args()
 fe = importlib.import_module("audio_style_transfer_b200.frontend").FrontEnd("cuda:0")
@@ -31,7 +32,7 @@ legs["stats"] = lambda: fe.stats_accumulate(wave, acc, counts, group_ids=gid)
 res = {}
 for name in a.legs.split(","):
     fn = legs[name]
-    for _ in range(3):
+    for _ in range(a.warmup):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
