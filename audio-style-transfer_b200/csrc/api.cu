@@ -308,9 +308,10 @@ int ast_stats_accumulate(const ast_plan* plan, const float* wave, const int32_t*
   OutSpec o = make_out(plan, nullptr, AST_LAYOUT_FLAT, t_dim, kFTotal, 0);
   const int stft_tiles = stft_tiles_per_clip(plan, batch, t_dim, /*stats_mode=*/true);
   if (stft_tiles > stats_stft_tiles_max(max_samples)) return fail(AST_ERR_WORKSPACE, "internal: statistics tile bound exceeded");
-  rc = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st, 0, false, nullptr, nullptr, 0, sc.part_stft,
-                   sc.part_n);
-  if (rc != AST_OK) return rc;
+  // same order as the feature call: decimator -> CQT projection (runs into the decimator's tail) -> STFT as the
+  // projection's programmatic dependent (it waits for nothing: it reads the waveform and writes its own partials, and
+  // its CTAs fill the SMs as the persistent CQT CTAs retire).  The finalise kernel is an ordinary launch: it starts
+  // when everything before it on the stream has completed.
   const long long ws_stride = cqt_ws_clip_stride(max_samples);
   rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, st);
   if (rc != AST_OK) return rc;
@@ -320,6 +321,10 @@ int ast_stats_accumulate(const ast_plan* plan, const float* wave, const int32_t*
   oq.cqt_part = sc.part_cqt;
   rc = launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride,
                   use_tc_decimator() ? w.dec_flags : nullptr, oq, st);
+  if (rc != AST_OK) return rc;
+  const bool chained = g_overlap_streams && !profile_on() && use_tc_decimator();
+  rc = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st, 0, /*pdl=*/chained, nullptr, nullptr, 0,
+                   sc.part_stft, sc.part_n);
   if (rc != AST_OK) return rc;
   rc = launch_stats_finalize_clips(sc.part_stft, sc.part_n, stft_tiles, sc.part_cqt, stats_cqt_tiles(max_samples), lengths,
                                    max_samples, batch, sc.clip_stats, st);

@@ -232,14 +232,14 @@ int launch_clip_stats(const float* feats, const int32_t* n_frames, int batch, in
 // (stft.cu: one per CTA tile of frames; cqt_tc.cu: one per 32-frame quadrant of a 128-frame tile).  One CTA per clip
 // merges them in frame order with Chan's formula in float64 and writes the clip's mean and UNBIASED variance
 // (compute_separated_stats.py:27-28) in the layout stats_accumulate_kernel adds up.
-__global__ void __launch_bounds__(256) stats_finalize_clips_kernel(const float2* __restrict__ part_stft,
+__global__ void __launch_bounds__(128) stats_finalize_clips_kernel(const float2* __restrict__ part_stft,
                                                                    const float* __restrict__ part_n, int stft_tiles,
                                                                    const float2* __restrict__ part_cqt, int cqt_tiles,
                                                                    const int32_t* __restrict__ lengths, long long max_samples,
                                                                    double* __restrict__ clip_stats) {
   const int b = blockIdx.x;
   const int frames = num_frames(lengths ? lengths[b] : max_samples);
-  for (int idx = threadIdx.x; idx < 2 * kFTotal; idx += blockDim.x) {
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < 2 * kFTotal; idx += gridDim.y * blockDim.x) {
     const int c = idx / kFTotal, f = idx - c * kFTotal;
     double n = 0.0, mean = 0.0, m2 = 0.0;
     auto merge = [&](double nb, float2 pm) {
@@ -275,8 +275,9 @@ int launch_stats_finalize_clips(const float2* part_stft, const float* part_n, in
                                 cudaStream_t st) {
   if (batch == 0) return AST_OK;
   ProfileSpan span("stats_finalize_clips_kernel", st);
-  stats_finalize_clips_kernel<<<batch, 256, 0, st>>>(part_stft, part_n, stft_tiles, part_cqt, cqt_tiles, lengths, max_samples,
-                                                     clip_stats);
+  // one thread per (clip, channel, bin): each walks its ~ 7 - 28 partials serially (latency bound), so spread them wide
+  stats_finalize_clips_kernel<<<dim3((unsigned)batch, (2 * kFTotal + 127) / 128), 128, 0, st>>>(
+      part_stft, part_n, stft_tiles, part_cqt, cqt_tiles, lengths, max_samples, clip_stats);
   AST_LAUNCH_CHECK("stats_finalize_clips_kernel");
   return AST_OK;
 }

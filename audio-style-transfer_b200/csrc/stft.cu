@@ -311,7 +311,7 @@ __device__ __forceinline__ unsigned long long stft_global_ns() {
 #endif
 
 template <int kMode>   // 0: features (normalise + store), 1: statistics (per-bin moments, nothing stored)
-__global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 2) stft_kernel(const StftParams p) {
+__global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 3) stft_kernel(const StftParams p) {
   extern __shared__ __align__(16) unsigned char stft_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float2* tile = reinterpret_cast<float2*>(stft_smem) + warp * kTileSize;
@@ -610,8 +610,12 @@ int launch_stft(const ast_plan* plan, const float* wave, const int32_t* lengths,
   ProfileSpan span("stft_kernel", st);
   if (stats_mode) {
     if ((int)grid.x != tiles) return fail(AST_ERR_INVALID_ARG, "internal: statistics tile count mismatch");
-    stft_kernel<1><<<grid, kStftThreads, kStftStatsSmem, st>>>(p);
-    AST_LAUNCH_CHECK("stft_kernel<stats>");
+    if (pdl) {   // behind the CQT projection of the statistics call, like the feature call's STFT
+      AST_CUDA_TRY(launch_with_pdl(stft_kernel<1>, grid, kStftThreads, kStftStatsSmem, st, p));
+    } else {
+      stft_kernel<1><<<grid, kStftThreads, kStftStatsSmem, st>>>(p);
+      AST_LAUNCH_CHECK("stft_kernel<stats>");
+    }
   } else if (pdl) {
     // programmatic dependent of the CQT projection launched just before it on the same stream: the kernel never
     // waits for it (disjoint output columns), so its CTAs fill the SMs as the persistent CQT CTAs retire
