@@ -104,3 +104,21 @@ def test_stats_command_writes_reference_npz(tmp_path):
     # the files load through the reference's contract
     m, s = dl.load_stats_npz(os.path.join(out_dir, "stats_unified_stft_cqt.npz"))
     assert tuple(m.shape) == (2, 597) and tuple(s.shape) == (2, 597)
+
+
+def test_synth_clips_are_a_pure_function_of_the_clip_id():
+    """ast_synth_clips (the configs[3] workload generator): any chunking / any rank regenerates the same clip bit for
+    bit, piano-like below violin_from_id and violin-like from there on, RMS near the dataset's 0.07."""
+    fe = importlib.import_module("audio_style_transfer_b200.frontend").FrontEnd("cuda:0")
+    whole = fe.synth_clips(12, first_clip_id=100, violin_from_id=106, n_samples=50000)
+    assert tuple(whole.shape) == (12, 50000) and whole.dtype == torch.float32
+    parts = torch.cat([fe.synth_clips(5, first_clip_id=100, violin_from_id=106, n_samples=50000),
+                       fe.synth_clips(7, first_clip_id=105, violin_from_id=106, n_samples=50000)])
+    assert torch.equal(whole, parts)
+    rms = whole.double().pow(2).mean(1).sqrt()
+    assert float(rms.min()) > 0.02 and float(rms.max()) < 0.2 and bool(torch.isfinite(whole).all())
+    assert not torch.equal(whole[0], whole[1])
+    # a prefix of a clip is the same clip (sample i depends on (id, i) only, up to the onset scaling by the length)
+    buf = torch.zeros((3, 50008), device="cuda")
+    out = fe.synth_clips(3, first_clip_id=100, violin_from_id=106, n_samples=50000, out=buf)
+    assert torch.equal(out, whole[:3]) and float(buf[:, 50000:].abs().max()) == 0.0
