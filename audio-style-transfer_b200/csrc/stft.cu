@@ -474,10 +474,27 @@ __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 3) 
         separate_and_emit(v, lane, emit);
       }
       STFT_STAMP(5);   // separation + normalisation + staging
+#ifdef AST_STFT_VECTOR_FLUSH   // diagnostic A/B: the staged rows leave as 16-byte vector stores instead of bulk copies
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float* staged = stage + j * kStageRow + ph[j];
+        const int head = (4 - ph[j]) & 3, body = (kFStft - head) & ~3, tail = kFStft - head - body;
+        if (lane < head) rows[j][lane] = staged[lane];
+        if (lane < tail) rows[j][head + body + lane] = staged[head + body + lane];
+        const float4* s4 = reinterpret_cast<const float4*>(staged + head);
+        float4* d4 = reinterpret_cast<float4*>(rows[j] + head);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (lane + 32 * i < body / 4) d4[lane + 32 * i] = s4[lane + 32 * i];
+      }
+      __syncwarp();
+#else
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the bulk-copy engine
       __syncwarp();
       flush_rows(rows, stage, ph, lane);
       bulk_commit();   // (per thread: lanes 7, 15, 23, 31 have one copy each in their group, the others an empty one)
+#endif
       STFT_STAMP(6);   // fence + flush
     } else
 #endif
