@@ -347,6 +347,9 @@ def stats_leg(fe, device, rank, world, dist, barrier):
     stats_pass(fe, stats_mod, range(0, min(500, total)), total, STATS_RESIDENT_CLIPS, STATS_BATCH)   # warm-up
     barrier()
     acc, counts, ms_compute = stats_pass(fe, stats_mod, shard, total, STATS_RESIDENT_CLIPS, STATS_BATCH)
+    if world > 1:   # NCCL sets its channels up lazily on the first collective of a size: not part of the all-reduce's time
+        for _ in range(3):
+            stats_mod.allreduce_accumulators(torch.zeros_like(acc), torch.zeros_like(counts))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -368,9 +371,15 @@ def stats_leg(fe, device, rank, world, dist, barrier):
             a, b = acc.cpu().numpy(), acc1.cpu().numpy()
             nz = np.abs(b) > 0
             rel = float((np.abs(a - b)[nz] / np.abs(b)[nz]).max()) if nz.any() else 0.0
+            # The per-clip moments are bit-identical on every rank (fixed tiles); only the ORDER of the float64 additions
+            # differs (N rank partials reduced by NCCL vs one running sum).  Sums of clip MEANS cancel (+/- terms), so
+            # an element-wise relative difference is unbounded by construction; the sums are compared relative to the
+            # largest accumulator of their kind (sum of means / sum of variances), as np.allclose(rtol, atol) would.
+            scaled = max(float(np.abs(a[:, k] - b[:, k]).max() / max(np.abs(b[:, k]).max(), 1e-300)) for k in (0, 1))
             res1 = stats_mod.finalize_all(acc1, counts1)
             same32 = all(np.array_equal(res[k][0], res1[k][0]) and np.array_equal(res[k][1], res1[k][1]) for k in res)
-            determinism = {"max_rel_diff_f64_sums": rel, "rtol": 1e-12, "ok": bool(rel <= 1e-12),
+            determinism = {"max_diff_over_max_accumulator": scaled, "rtol": 1e-12, "ok": bool(scaled <= 1e-12),
+                           "max_rel_diff_elementwise": rel,
                            "counts_equal": bool(np.array_equal(counts.cpu().numpy(), counts1.cpu().numpy())),
                            "float32_mean_std_bit_identical": bool(same32),
                            "how": f"rank 0 repeated all {total} clips alone and compared with the {world}-rank all-reduced sums"}
