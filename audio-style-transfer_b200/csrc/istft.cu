@@ -77,37 +77,51 @@ __device__ __forceinline__ float2 load_bin(const FrameRows& f, long long plane, 
 // The 16 inputs of a thread: all loads of a batch are issued before the first value is used (ncu: the kernel's
 // dominant stall is the long scoreboard on these loads, one round trip per batch).  Two batches of eight inputs per
 // pair: 32 loads each, 64 when a frame lies inside a section overlap (second section row to be averaged in).
+// Row pointers of one frame as the loads want them: bin 64 n + tid (n < 8) is lo[64 n], bin 64 (16 - n) - tid (n >= 8) is
+// hi[64 (16 - n)] - every load is [pointer + immediate].  (Round 1 formed each address as base + 64-bit index: 700 of the
+// kernel's 2 600 warp instructions per frame pair were integer address arithmetic.)
+struct RowPtrs {
+  const float* re_lo;
+  const float* re_hi;
+  const float* im_lo;
+  const float* im_hi;
+};
+__device__ __forceinline__ RowPtrs row_ptrs(const float* row, long long plane, int tid) {
+  RowPtrs r;
+  r.re_lo = row + tid;
+  r.re_hi = row - tid;
+  r.im_lo = r.re_lo + plane;
+  r.im_hi = r.re_hi + plane;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ float load_re(const RowPtrs& r) { return N < 8 ? __ldg(r.re_lo + 64 * N) : __ldg(r.re_hi + 64 * (16 - N)); }
+template <int N>
+__device__ __forceinline__ float load_im(const RowPtrs& r) { return N < 8 ? __ldg(r.im_lo + 64 * N) : __ldg(r.im_hi + 64 * (16 - N)); }
+
+template <int N0, int I, int CNT>
+struct LoadRow {   // compile-time loop over the CNT inputs N0 .. N0 + CNT - 1 of a batch
+  static __device__ __forceinline__ void run(const RowPtrs& r, bool on, float (&re)[CNT], float (&im)[CNT]) {
+    re[I] = on ? load_re<N0 + I>(r) : 0.f;
+    im[I] = on ? load_im<N0 + I>(r) : 0.f;
+    if constexpr (I + 1 < CNT) LoadRow<N0, I + 1, CNT>::run(r, on, re, im);
+  }
+};
+
 template <int N0, int CNT, bool kDup>
 __device__ __forceinline__ void load_inputs(float2 (&v)[16], int tid, const FrameRows& fa, const FrameRows& fb,
                                             long long plane, bool live_b) {
   float are[CNT], aim[CNT], bre[CNT], bim[CNT];
-  int kk[CNT];
-#pragma unroll
-  for (int i = 0; i < CNT; ++i) kk[i] = (N0 + i) < 8 ? 64 * (N0 + i) + tid : 64 * (16 - (N0 + i)) - tid;
-#pragma unroll
-  for (int i = 0; i < CNT; ++i) {
-    are[i] = __ldg(fa.r0 + kk[i]);
-    aim[i] = __ldg(fa.r0 + plane + kk[i]);
-  }
-#pragma unroll
-  for (int i = 0; i < CNT; ++i) {
-    bre[i] = live_b ? __ldg(fb.r0 + kk[i]) : 0.f;
-    bim[i] = live_b ? __ldg(fb.r0 + plane + kk[i]) : 0.f;
-  }
+  const RowPtrs pa = row_ptrs(fa.r0, plane, tid), pb = row_ptrs(fb.r0, plane, tid);
+  LoadRow<N0, 0, CNT>::run(pa, true, are, aim);
+  LoadRow<N0, 0, CNT>::run(pb, live_b, bre, bim);
   if (kDup) {
     // the second section row of an overlap frame is loaded in the same batch (predicated off elsewhere), not after it
     const bool dup_a = fa.r1 != nullptr, dup_b = live_b && fb.r1 != nullptr;
     float are1[CNT], aim1[CNT], bre1[CNT], bim1[CNT];
-#pragma unroll
-    for (int i = 0; i < CNT; ++i) {
-      are1[i] = dup_a ? __ldg(fa.r1 + kk[i]) : 0.f;
-      aim1[i] = dup_a ? __ldg(fa.r1 + plane + kk[i]) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < CNT; ++i) {
-      bre1[i] = dup_b ? __ldg(fb.r1 + kk[i]) : 0.f;
-      bim1[i] = dup_b ? __ldg(fb.r1 + plane + kk[i]) : 0.f;
-    }
+    const RowPtrs pa1 = row_ptrs(dup_a ? fa.r1 : fa.r0, plane, tid), pb1 = row_ptrs(dup_b ? fb.r1 : fb.r0, plane, tid);
+    LoadRow<N0, 0, CNT>::run(pa1, dup_a, are1, aim1);
+    LoadRow<N0, 0, CNT>::run(pb1, dup_b, bre1, bim1);
     if (dup_a) {  // ascending section order like the reference's += loop, then / count (= 2)
 #pragma unroll
       for (int i = 0; i < CNT; ++i) {

@@ -501,6 +501,25 @@ def test_full_batch_against_oracle(fe, piano_stats):
     assert worst_s <= 1e-5 and worst_c <= 1e-5, (worst_s, worst_c)
 
 
+def test_rows_that_are_not_16_byte_aligned_take_the_register_path(fe):
+    """A batch whose row stride is not a multiple of 4 floats cannot be described by a tensor map: the CQT projection
+    falls back to its register-staged producers (cqt_tc_kernel<0>) and must give the same numbers as the TMA path gives
+    on an aligned copy of the same clips."""
+    base = synth.batch(3, 40002)                      # stride 40002: 8-byte aligned rows only
+    x = cuda(base)
+    assert x.stride(0) % 4 == 2
+    got, _ = fe.features(x, layout="flat")
+    padded = torch.zeros((3, 40004), device="cuda")
+    padded[:, :40002] = x
+    ref, _ = fe.features(padded[:, :40002], layout="flat")   # stride 40004: TMA path
+    assert padded[:, :40002].stride(0) % 4 == 0
+    assert torch.equal(got[..., :513], ref[..., :513])
+    assert (got[..., 513:] - ref[..., 513:]).abs().max() <= 1e-5 * ref[..., 513:].abs().max()
+    V = oc.cqt(base[1])
+    want = np.stack([V.real.T, V.imag.T])
+    assert rel_max(got[1, :, :, 513:].cpu().numpy(), want) <= 1e-5
+
+
 def test_features_host_pipeline_equals_device_call(fe, piano_stats):
     """The host-buffer API (chunked H2D / kernels / D2H over several streams) returns exactly what the
     device-resident call returns, for chunk sizes that do and do not divide the batch."""
@@ -537,7 +556,7 @@ def test_features_host_full_size_chunks_repeatedly(fe, piano_stats):
 
 
 @pytest.mark.parametrize("env", [{"AST_DECIMATOR": "fma"}, {"AST_CQT": "fma"}, {"AST_DECIMATOR": "fma", "AST_CQT": "fma"},
-                                 {"AST_OVERLAP": "0"}])
+                                 {"AST_OVERLAP": "0"}, {"AST_CQT_TMA": "0"}])
 def test_diagnostic_kernel_variants_agree(fe, tmp_path, env):
     """The FMA-pipe twins of the two tensor-core kernels (AST_DECIMATOR=fma, AST_CQT=fma) and the serial launch order
     (AST_OVERLAP=0) are diagnostics of the same library, selected when a plan is created: run them in a fresh process
