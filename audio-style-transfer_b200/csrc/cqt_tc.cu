@@ -167,6 +167,12 @@ __device__ __forceinline__ void decode_tile(const CqtTcParams& p, int tile, int&
   t0 = (rem - b * p.tiles_per_clip_oct) * cqt_tc::kM;
 }
 
+// A tile none of whose 128 frames exists in its clip (ragged batch: the clip is shorter than the padded length).  Every
+// role skips it - no boxes, no MMAs, no accumulator hand-over - except the epilogue, which writes its rows as zeros.
+__device__ __forceinline__ bool tile_dead(const CqtTcParams& p, int b, int t0) {
+  return p.lengths != nullptr && t0 >= num_frames(p.lengths[b]);
+}
+
 // tid: thread index within its producer group (0..95)
 __device__ __forceinline__ BlockPlan plan_block(const CqtTcParams& p, int b, int oct, int t0, int j, int tid,
                                                 unsigned stages_complete) {
@@ -447,6 +453,7 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         int b, oct, t0;
         decode_tile(p, tile, b, oct, t0);
+        if (tile_dead(p, b, t0)) continue;
         const int hop = kHop >> oct, rt = block_rt(oct), cols = block_cols(oct);
         const int n_units = cols * rt;
         const long long len0 = p.lengths ? p.lengths[b] : p.max_samples;
@@ -537,6 +544,7 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         int b, oct, t0;
         decode_tile(p, tile, b, oct, t0);
+        if (tile_dead(p, b, t0)) continue;
         const int hop = kHop >> oct;
         const int n_blocks = blocks_per_tile(oct);
         const int cols = block_cols(oct), rt = block_rt(oct);
@@ -617,10 +625,11 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
     const uint32_t idesc64 = umma::instr_desc_tf32(kM, 2 * kN), idesc32 = umma::instr_desc_tf32(kM, kN);
     const uint32_t b_addr = umma::smem_u32(b_img);
     int item = 0, n_tile = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++n_tile) {
-      const int q = n_tile & 1;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       int b, oct, t0;
       decode_tile(p, tile, b, oct, t0);
+      if (kTma && tile_dead(p, b, t0)) continue;   // n_tile counts the tiles that use an accumulator set
+      const int q = n_tile & 1;
       umma::mbar_wait(acc_empty + q, ((n_tile >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator set
       umma::fence_after_thread_sync();
       const int n_blocks = oct == 0 ? 8 : oct == 1 ? 4 : oct == 2 ? 2 : 1;
@@ -656,6 +665,7 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
         __syncwarp();
         AST_STAMP(1, item, 2);
       }
+      ++n_tile;
     }
   } else if (warp >= kEpilogueWarp0) {
     // ================================================================= epilogue (warps 8-15)
@@ -714,28 +724,32 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
       }
       return c;
     };
-    const int stride2 = kEpiGroups * (int)gridDim.x;
-    // Rotation with ONE load_ctx site (code size: the epilogue's loop is the kernel's largest): an iteration first loads
-    // the context of the tile AFTER the one it is about to drain - before it waits for that tile's accumulators, so the
-    // context's global loads overlap the wait - then processes the current tile.
-    TileCtx ctx, nxt;
-    ctx.flags = 0;
-    for (int k = -1, tile = blockIdx.x + group * (int)gridDim.x - stride2;; tile += stride2, ++k) {
-      const bool has_next = tile + stride2 < total;
-      if (has_next) nxt = load_ctx(tile + stride2);
-      if (k < 0) {
-        if (!has_next) break;
-        ctx = nxt;
-        continue;
+    // Every epilogue warp walks ALL of the CTA's tiles; the accumulator set, barrier phase and group of a live tile follow
+    // the number of live tiles before it (the MMA warp counts the same way).
+    // The tile's context is loaded BEFORE the wait for its accumulators, so its global loads overlap the wait.
+    TileCtx ctx;
+    int n_live = 0;
+    for (int n_pos = 0, tile = blockIdx.x; tile < total; tile += gridDim.x, ++n_pos) {
+      bool dead = false;
+      if (kTma) {
+        int b, oct, t0;
+        decode_tile(p, tile, b, oct, t0);
+        dead = tile_dead(p, b, t0);
       }
-      const int n_tile = kEpiGroups * k + group;
+      const int n_tile = n_live;   // sequence number among the tiles that use an accumulator set
+      if (!dead) ++n_live;
+      // live tiles go to the groups in LIVE order, so that an accumulator set is always drained by the same group, in
+      // order (a parity wait of a later use must not overtake an earlier one); dead tiles by position
+      if ((dead ? n_pos : n_tile) % kEpiGroups != group) continue;
+      ctx = load_ctx(tile);
       const int set = n_tile & 1;   // accumulator set of this tile
+      float acc[kCqtCols];
+      if (!dead) {
       if (warp == kEpilogueWarp0) AST_STAMP(2, n_tile, 0);
       umma::mbar_wait(acc_full + set, (n_tile >> 1) & 1);
       umma::fence_after_thread_sync();
       if (warp == kEpilogueWarp0) AST_STAMP(2, n_tile, 1);
       // 24 of each accumulator's 32 columns carry data: one x16 and one x8 load per part
-      float acc[kCqtCols];
       const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(set * kSetCols);
       {
         float a16[16], a8[8];
@@ -772,6 +786,7 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
         if (p.out.stats) v = (v - mu) * rs;
         stg[lane * kEpiStride + c] = v;
       }
+      }   // (a dead tile has no accumulators: its rows are stored as zeros / its partial moments are empty below)
       __syncwarp();
       if (warp == kEpilogueWarp0) AST_STAMP(2, n_tile, 4);
       if (warp == kEpilogueWarp0) AST_STAMP(2, n_tile, 5);
@@ -788,8 +803,6 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
           p.out.cqt_part[ctx.part_idx + lane] = make_float2(mean, m2);
         }
         __syncwarp();
-        if (!has_next) break;
-        ctx = nxt;
         continue;
       }
       // 32 rows x 12 columns per plane = 12 store rounds; lane l of round i owns element 32 i + l
@@ -813,8 +826,6 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
       }
       __syncwarp();  // the staging buffer is rewritten by the next tile
       if (warp == kEpilogueWarp0) AST_STAMP(2, n_tile, 3);
-      if (!has_next) break;
-      ctx = nxt;
     }
   }
   umma::fence_before_thread_sync();
