@@ -6,6 +6,34 @@
 #include "../../include/ast_frontend.h"
 #include "fft_core.h"
 
+// Diagnostic build only (-DAST_TIMELINE, scratch/timeline.py): every CTA of the three feature kernels stamps its start and
+// end (%globaltimer) and its SM, per kernel, so the whole call can be drawn as a Gantt chart.
+#ifdef AST_TIMELINE
+#define AST_TIMELINE_DEFINE(name)                                                                          \
+  __device__ unsigned long long g_tl_##name[8192][4];                                                      \
+  extern "C" int ast_debug_timeline_##name(unsigned long long* host) {                                     \
+    return (int)cudaMemcpyFromSymbol(host, g_tl_##name, sizeof(g_tl_##name));                              \
+  }
+#define AST_TIMELINE_STAMP(name, cta, k) AST_TIMELINE_STAMP_IF(threadIdx.x == 0, name, cta, k)
+#define AST_TIMELINE_STAMP_IF(pred, name, cta, k)                                                          \
+  do {                                                                                                     \
+    if ((pred) && (cta) < 8192) {                                                                          \
+      unsigned long long t_;                                                                               \
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                                                \
+      g_tl_##name[cta][k] = t_;                                                                            \
+      if ((k) == 0) {                                                                                      \
+        unsigned s_;                                                                                       \
+        asm volatile("mov.u32 %0, %smid;" : "=r"(s_));                                                     \
+        g_tl_##name[cta][2] = s_;                                                                          \
+      }                                                                                                    \
+    }                                                                                                      \
+  } while (0)
+#else
+#define AST_TIMELINE_DEFINE(name)
+#define AST_TIMELINE_STAMP(name, cta, k) do {} while (0)
+#define AST_TIMELINE_STAMP_IF(pred, name, cta, k) do {} while (0)
+#endif
+
 namespace ast {
 
 constexpr int kNfft = AST_N_FFT;

@@ -297,6 +297,8 @@ __device__ __noinline__ void issue_block_any(int oct, uint32_t a_hi_addr, uint32
   }
 }
 
+AST_TIMELINE_DEFINE(cqt)
+
 template <bool kTma>
 __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads, 1)
     cqt_tc_kernel(const __grid_constant__ CqtTcParams p) {
@@ -321,6 +323,7 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  AST_TIMELINE_STAMP(cqt, blockIdx.x, 0);
   pdl_launch_dependents();
   // B images: resident for the CTA's lifetime
   for (int i = tid; i < kBFloats / 4; i += (int)blockDim.x)
@@ -830,7 +833,9 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
   }
   umma::fence_before_thread_sync();
   __syncthreads();
+  AST_TIMELINE_STAMP_IF(warp == kMmaWarp && lane == 0, cqt, blockIdx.x, 1);
   if (warp == kMmaWarp) umma::tmem_dealloc(tmem_base, kTmemCols);
+  AST_TIMELINE_STAMP_IF(warp == kMmaWarp && lane == 0, cqt, blockIdx.x, 3);   // (after the TMEM release)
   // The projection has consumed every decimator tile, but the decimator's publisher bumps a tile's flag BEFORE its
   // stage counter: formally that grid may still be executing its last atomicAdd.  Each CTA therefore waits for its
   // programmatic primary before it exits, so "the CQT grid is complete" implies "the decimator grid is complete" -

@@ -93,6 +93,8 @@ __device__ long long g_dec_trace[4][64][8];
 #define DTC_STAMP(role, idx, k) do {} while (0)
 #endif
 
+AST_TIMELINE_DEFINE(dec)
+
 struct DecimateTcParams {
   const float* wave;       // octave 0: clip b at wave + b * wave_stride
   long long wave_stride;
@@ -104,6 +106,8 @@ struct DecimateTcParams {
   int batch;
   int tiles_per_clip[kDecStages];
   int tile_prefix[kDecStages + 1];   // first tile number of each stage; [6] = total
+  int tail_stage;                    // first stage whose tiles are dealt to the last tail_ctas CTAs only (6: none)
+  int tail_ctas;
   bool vec_ok0;                      // 16-byte loads legal on the octave-0 rows
   int* flags;                        // [stage][clip][tile of stage 0's count]: epilogue warps that finished the tile (4 = done)
   const float* strip_hi;   // [2][320][4] smem image of the Toeplitz strip (TF32-exact values)
@@ -149,8 +153,40 @@ __device__ __forceinline__ DtcTile dtc_decode(const DecimateTcParams& p, int til
   return t;
 }
 
+// Dealing of the tiles to the CTAs.  Tiles below tile_prefix[tail_stage] ("early": the stages with many tiles per clip)
+// go round-robin to every CTA.  The stages with at most two tiles per clip form a dependent chain per clip that no
+// amount of parallelism shortens; spread over the whole grid they would keep (nearly) every SM occupied by a mostly
+// idle CTA until the chain's end.  They are dealt to the LAST tail_ctas CTAs only (those have one early tile fewer),
+// CTA j taking the clips j, j + tail_ctas, ...: stage by stage, clip by clip, so its list is still ascending in tile
+// number (the progress argument in the header) and a clip's chain stays on one CTA.  The other CTAs exit early and their
+// SMs go to the dependent launches (the CQT projection's octave-0 tiles, then the STFT).
+__device__ __forceinline__ int dtc_tail_first(const DecimateTcParams& p, int total) {
+  const int j = (int)blockIdx.x - ((int)gridDim.x - p.tail_ctas);
+  if (p.tail_stage >= kDecStages || j < 0 || j >= p.batch) return total;
+  return p.tile_prefix[p.tail_stage] + j * p.tiles_per_clip[p.tail_stage];
+}
+__device__ __forceinline__ int dtc_first(const DecimateTcParams& p, int total) {
+  const int early = p.tile_prefix[p.tail_stage];
+  return (int)blockIdx.x < early ? (int)blockIdx.x : dtc_tail_first(p, total);
+}
+__device__ __forceinline__ int dtc_step(const DecimateTcParams& p, int tile, int total) {   // total: end of the list
+  const int early = p.tile_prefix[p.tail_stage];
+  if (tile < early) {
+    tile += gridDim.x;
+    return tile < early ? tile : dtc_tail_first(p, total);
+  }
+  int s = p.tail_stage;
+  for (int i = p.tail_stage + 1; i < kDecStages; ++i) s += tile >= p.tile_prefix[i] ? 1 : 0;
+  const int r = tile - p.tile_prefix[s];
+  int b = r / p.tiles_per_clip[s];
+  if (r - b * p.tiles_per_clip[s] + 1 < p.tiles_per_clip[s]) return tile + 1;
+  b += p.tail_ctas;
+  if (b < p.batch) return p.tile_prefix[s] + b * p.tiles_per_clip[s];
+  if (++s == kDecStages) return total;
+  return p.tile_prefix[s] + ((int)blockIdx.x - ((int)gridDim.x - p.tail_ctas)) * p.tiles_per_clip[s];
+}
 __device__ __forceinline__ int dtc_next_live(const DecimateTcParams& p, int tile, int total) {
-  for (tile += gridDim.x; tile < total; tile += gridDim.x)
+  for (tile = dtc_step(p, tile, total); tile < total; tile = dtc_step(p, tile, total))
     if (dtc_decode(p, tile).live) return tile;
   return -1;
 }
@@ -263,6 +299,7 @@ __device__ __forceinline__ void dtc_load_slice(const DtcTile& t, int tg, int s, 
 __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const DecimateTcParams p) {
   using namespace dtc;
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  AST_TIMELINE_STAMP(dec, blockIdx.x, 0);
   float* a_hi = reinterpret_cast<float*>(smem_raw);      // [2 tiles][4 slices][8 chunk columns][129 rows][4]
   float* a_lo = a_hi + 2 * kTileFloats;                  // [2 stages][8][129][4]
   float* t_hi = a_lo + 2 * kSliceFloats;
@@ -310,7 +347,7 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
   pdl_wait();
   pdl_launch_dependents();
   const int total = p.tile_prefix[kDecStages];
-  int tile = blockIdx.x;
+  int tile = dtc_first(p, total);
   if (tile < total && !dtc_decode(p, tile).live) tile = dtc_next_live(p, tile, total);
 
   if (warp < kProducers / 32) {
@@ -492,7 +529,7 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
     // seen a stage complete (counter == tiles of the stage) stops polling per-tile counters for it.
     int* stage_done = p.flags + (long long)kDecStages * p.batch * p.tiles_per_clip[0];
     int n = 0;
-    for (int g = blockIdx.x; g < total; g += gridDim.x) {
+    for (int g = dtc_first(p, total); g < total; g = dtc_step(p, g, total)) {
       const DtcTile t = dtc_decode(p, g);
       if (lane == 0) {
         if (t.live) {
@@ -516,7 +553,9 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
   }
   umma::fence_before_thread_sync();
   __syncthreads();
+  AST_TIMELINE_STAMP_IF(warp == kMmaWarp && lane == 0, dec, blockIdx.x, 1);
   if (warp == kMmaWarp) umma::tmem_dealloc(tmem_base, kTmemCols);
+  AST_TIMELINE_STAMP_IF(warp == kMmaWarp && lane == 0, dec, blockIdx.x, 3);   // (after the TMEM release)
 }
 
 int decimate_init() {
@@ -615,6 +654,22 @@ int launch_decimate_cascade_tc(const ast_plan* plan, const float* wave, const in
   if (!flags_zeroed) AST_CUDA_TRY(cudaMemsetAsync(flags, 0, decimator_flag_bytes(batch, max_samples), st));
   long long ctas = total;
   if (ctas > plan->sm_count) ctas = plan->sm_count;  // persistent and co-resident: one CTA per SM (tiles wait on each other)
+  // the chain stages (<= 2 tiles per clip) on one CTA per clip, when that leaves at least half of the grid free to go
+  p.tail_stage = kDecStages;
+  p.tail_ctas = 0;
+  {
+    // measured at 64 clips (scratch/tail_sweep.sh): off 0.3015 ms per feature step, 64 CTAs 0.2980, 32 (two clips per
+    // CTA) 0.2952 but a slower statistics call, 16 0.3148: a chain costs ~ 35 us of latency + 15 us per clip on its CTA
+    int want = 64, clips_per_cta = 1;
+    if (const char* env = getenv("AST_DEC_TAIL_CTAS")) want = atoi(env), clips_per_cta = 16;   // diagnostic sweep
+    int first_chain = kDecStages;
+    while (first_chain > 0 && p.tiles_per_clip[first_chain - 1] <= 2) --first_chain;
+    const int k = batch < want ? batch : want;
+    if (k > 0 && first_chain < kDecStages && first_chain > 0 && 2 * k <= ctas && batch <= clips_per_cta * k) {
+      p.tail_stage = first_chain;
+      p.tail_ctas = k;
+    }
+  }
   ProfileSpan span("decimate2_tc_kernel", st);
   AST_CUDA_TRY(launch_with_pdl(decimate2_tc_kernel, dim3((unsigned)ctas), dtc::kThreads, dtc::kSmem, st, p));
   return AST_OK;

@@ -310,6 +310,8 @@ __device__ __forceinline__ unsigned long long stft_global_ns() {
 #define STFT_STAMP(k) do {} while (0)
 #endif
 
+AST_TIMELINE_DEFINE(stft)
+
 template <int kMode>   // 0: features (normalise + store), 1: statistics (per-bin moments, nothing stored)
 __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 3) stft_kernel(const StftParams p) {
   extern __shared__ __align__(16) unsigned char stft_smem[];
@@ -317,6 +319,7 @@ __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 3) 
   float2* tile = reinterpret_cast<float2*>(stft_smem) + warp * kTileSize;
   float4* acc = reinterpret_cast<float4*>(stft_smem + kStftSmem) + warp * kAccStride;   // statistics mode only
   float* warp_n = reinterpret_cast<float*>(stft_smem + kStftSmem + sizeof(float4) * kStftWarps * kAccStride);
+  if (kMode == 0) AST_TIMELINE_STAMP(stft, blockIdx.x + gridDim.x * blockIdx.y, 0);
   pdl_launch_dependents();
   const int b = blockIdx.y;
   const int len = (int)(p.lengths ? p.lengths[b] : p.max_samples);
@@ -545,6 +548,7 @@ __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 3) 
       if (k == 0) p.part_n[tile_id] = (float)n;
     }
   }
+  if (kMode == 0) AST_TIMELINE_STAMP(stft, blockIdx.x + gridDim.x * blockIdx.y, 1);   // (warp 0's end)
   if (p.tail_counter) {
     // This grid never waited for its programmatic primary (the CQT projection) and may finish before it.  The last CTA
     // to get here waits for that grid, so the STFT - the feature call's last kernel - cannot COMPLETE before the call's
@@ -561,6 +565,8 @@ static int g_stft_ctas_per_sm = AST_STFT_CTAS;
 
 int stft_init() {
   AST_CUDA_TRY(cudaFuncSetAttribute(stft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStftSmem));
+  if (const char* env = getenv("AST_STFT_CARVEOUT"))   // diagnostic: shared-memory share of the unified L1 / shared array, %
+    AST_CUDA_TRY(cudaFuncSetAttribute(stft_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(env)));
   AST_CUDA_TRY(cudaFuncSetAttribute(stft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStftStatsSmem));
   int n = 0;
   AST_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stft_kernel<0>, kStftThreads, kStftSmem));

@@ -106,6 +106,7 @@ def test_stats_command_writes_reference_npz(tmp_path):
     assert tuple(m.shape) == (2, 597) and tuple(s.shape) == (2, 597)
 
 
+@pytest.mark.gpu
 def test_synth_clips_are_a_pure_function_of_the_clip_id():
     """ast_synth_clips (the configs[3] workload generator): any chunking / any rank regenerates the same clip bit for
     bit, piano-like below violin_from_id and violin-like from there on, RMS near the dataset's 0.07."""
