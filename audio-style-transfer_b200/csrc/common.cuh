@@ -196,6 +196,8 @@ struct ast_plan {
   float* d_cqt_tc_images;  // CQT kernel as TF32 hi / lo B-operand images per pass (cqt_tc.cu)
   float* d_dec_strip_hi;  // decimator Toeplitz strip, TF32 hi part (smem image, decimate.cu)
   float* d_dec_strip_lo;  // ... and the TF32 residual
+  uint16_t* d_dec_strip_h_hi;  // the FP16-split kernel's strip (taps x 2^15 as FP16) and its FP16 residual
+  uint16_t* d_dec_strip_h_lo;
 };
 
 namespace ast {
@@ -244,6 +246,9 @@ void set_overlap_streams(int on);
 bool use_tc_cqt();
 int decimator_strip_floats();
 void host_decimator_strip(const double* taps_scaled, float* strip_hi, float* strip_lo);  // decimator_strip_floats() each
+int decimator_strip_h_bytes();
+void host_decimator_strip_h(const double* taps_scaled, uint16_t* strip_hi, uint16_t* strip_lo);  // decimator_strip_h_bytes() each
+void set_decimator_half(int on);
 size_t decimator_flag_bytes(int batch, long long max_samples);
 int decimator_tile_outputs();                       // outputs per decimator tile (7424)
 int decimator_tiles_stage0(long long max_samples);  // tiles per clip of the first stage = row stride of the flag array

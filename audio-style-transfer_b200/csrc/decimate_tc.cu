@@ -45,6 +45,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
+#include <cmath>
+
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -85,10 +88,13 @@ constexpr size_t kSmem = sizeof(float) * (2 * kTileFloats + 2 * kSliceFloats + 2
 constexpr int kDecStages = kOctaves - 1;  // 6
 
 #ifdef AST_TRACE
-// diagnostic build only (scratch/trace_dec.py): clock64 stamps of CTA 0's pipeline roles, per tile
+#ifndef AST_TRACE_CTA
+#define AST_TRACE_CTA 0   // 147: a CTA that runs a clip's chain stages
+#endif
+// diagnostic build only (scratch/trace_dec.py): clock64 stamps of one CTA's pipeline roles, per tile
 __device__ long long g_dec_trace[4][64][8];
 #define DTC_STAMP(role, idx, k) \
-  do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (idx) < 64) g_dec_trace[role][idx][k] = clock64(); } while (0)
+  do { if (blockIdx.x == (AST_TRACE_CTA) && (threadIdx.x & 31) == 0 && (idx) < 64) g_dec_trace[role][idx][k] = clock64(); } while (0)
 #else
 #define DTC_STAMP(role, idx, k) do {} while (0)
 #endif
@@ -112,6 +118,8 @@ struct DecimateTcParams {
   int* flags;                        // [stage][clip][tile of stage 0's count]: epilogue warps that finished the tile (4 = done)
   const float* strip_hi;   // [2][320][4] smem image of the Toeplitz strip (TF32-exact values)
   const float* strip_lo;
+  const uint4* strip_h_hi; // FP16-split kernel: [2][320][8 halves] image of the Toeplitz strip x 2^15, and its residual
+  const uint4* strip_h_lo;
   int debug;               // diagnostic bit mask (AST_DEC_DEBUG): 1 no epilogue shuffles / stores, 2 no producer loads, 4 no MMAs
 };
 
@@ -558,8 +566,349 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
   AST_TIMELINE_STAMP_IF(warp == kMmaWarp && lane == 0, dec, blockIdx.x, 3);   // (after the TMEM release)
 }
 
+
+// =====================================================================================================================
+// FP16-split variant (default).  The same GEMM, tiles, dependency protocol and epilogue; the operands are split into
+// FP16 pairs instead of TF32 pairs: FP16 and TF32 carry the same 11 significand bits, so  x = hi + lo,  g = hi + lo  with
+// three products (lo*hi, hi*lo, hi*hi) has the accuracy of the TF32 scheme, but a kind::f16 MMA contracts K = 16 per
+// instruction at the cost of a K = 8 kind::tf32 one: 24 MMAs per tile instead of 48, and half the operand bytes in
+// shared memory (138 KB per CTA instead of 220 KB).  FP16 has 5 exponent bits, so operands are scaled by powers of two
+// (exact) into its range: the taps by 2^15 on the host, the samples PER TILE by 2^k with k chosen from the tile's own
+// largest magnitude (producers: register max -> redux -> shared atomicMax -> one named barrier per tile) so that it lies
+// in [2^8, 2^9); residuals that fall into FP16's subnormal range are then below 2^-33 of the tile's largest sample.  The
+// epilogue multiplies the accumulator by 2^(-k-15).
+namespace dth {
+using dtc::kM; using dtc::kN; using dtc::kP; using dtc::kRS; using dtc::kGroupValid; using dtc::kGroups; using dtc::kRowsOut;
+using dtc::kSlices; using dtc::kProducers; using dtc::kEpilogueWarp0; using dtc::kMmaWarp; using dtc::kPublishWarp;
+using dtc::kThreads; using dtc::kTmemCols; using dtc::kProducerGroup; using dtc::kEpiStride; using dtc::kEpiFloats;
+constexpr int kRT = 130;                       // 16-byte rows per chunk column (2 mod 8: the producers' 4 chunks x 8 rows stores are conflict-free)
+constexpr int kSliceChunks = 4;                // 16-byte chunks (8 halves) per row per 32-sample slice
+constexpr int kKStepsPerSlice = 2;             // K = 16 per MMA
+constexpr int kSliceBytes = kSliceChunks * kRT * 16;   // 8 320
+constexpr int kTileBytes = kSlices * kSliceBytes;      // 33 280: A_hi of one tile
+constexpr int kStripRows = 320;                // 312 used: jj = -248 ... 63
+constexpr int kStripRow0 = 56;                 // strip row of (n = 0, gs = 0): jj = -192
+constexpr int kStripBytes = 2 * kStripRows * 16;
+constexpr int kTapShift = 15;                  // taps are staged as g * 2^15 (largest tap ~ 0.65)
+constexpr int kChunksPerThread = kM * kSliceChunks / kProducerGroup;   // 4 shared-memory chunks (8 samples each) per slice
+constexpr size_t kSmem = 2 * kTileBytes + 2 * kSliceBytes + 2 * kStripBytes + sizeof(float) * kEpiFloats + 256;
+}  // namespace dth
+
+__host__ __device__ constexpr uint32_t instr_desc_f16(int m, int n) {   // kind::f16, A = B = FP16, FP32 accumulate, K-major
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// One 32-sample slice of a tile for a producer thread: shared-memory chunk cc = tg & 3 (samples 8 cc .. 8 cc + 7 of the
+// slice) of the four rows rho = (tg >> 2) + 32 i, i.e. lane row tg >> 2 of row group i.  v[8 J + 2 i + h]: half h of it.
+template <int J>
+__device__ __forceinline__ void dth_load_slice(const DtcTile& t, int tg, int s, float4 (&v)[16]) {
+  using namespace dth;
+  const int a0 = kRS * (t.row0 + (tg >> 2)) - kDecHalf + 32 * s + 8 * (tg & 3);
+  if (t.debug & 2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[8 * J + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < kChunksPerThread; ++i) {
+    const int a = a0 + kRS * kGroupValid * i;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      v[8 * J + 2 * i + h] = t.interior ? ld_cg_f4(t.x + a + 4 * h) : dtc_load4(t.x, a + 4 * h, t.len_in, t.vec_ok);
+  }
+}
+
+// 8 samples x scale -> FP16 hi and FP16 residual images (one 16-byte chunk each)
+__device__ __forceinline__ void dth_split8(const float4& a, const float4& b, float scale, uint4& hi, uint4& lo) {
+  const float x[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+    const float2 back = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x[2 * i] - back.x, x[2 * i + 1] - back.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_h_kernel(const DecimateTcParams p) {
+  using namespace dth;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  AST_TIMELINE_STAMP(dec, blockIdx.x, 0);
+  unsigned char* a_hi = smem_raw;                            // [2 tiles][4 slices][4 chunk columns][130 rows][8 halves]
+  unsigned char* a_lo = a_hi + 2 * kTileBytes;               // [2 stages][4][130][8]
+  unsigned char* t_hi = a_lo + 2 * kSliceBytes;
+  unsigned char* t_lo = t_hi + kStripBytes;
+  float* epi_buf = reinterpret_cast<float*>(t_lo + kStripBytes);   // [4 warps][32 rows][68] epilogue transpose
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + kEpiFloats);
+  uint64_t* l_full = bars;          // (the barrier set of decimate2_tc_kernel)
+  uint64_t* l_empty = bars + 4;
+  uint64_t* h_empty = bars + 8;
+  uint64_t* acc_full = bars + 10;
+  uint64_t* acc_empty = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  unsigned int* stored_count = reinterpret_cast<unsigned int*>(bars + 15);
+  unsigned int* tile_max = reinterpret_cast<unsigned int*>(bars + 16);   // [3] bits of the largest |sample| of tiles n, n + 1, n + 2
+  float* tile_inv = reinterpret_cast<float*>(bars + 18);                 // [4] 2^(-k - 15) of the last four tiles
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < kStripBytes / 16; i += kThreads) {
+    reinterpret_cast<uint4*>(t_hi)[i] = __ldg(p.strip_h_hi + i);
+    reinterpret_cast<uint4*>(t_lo)[i] = __ldg(p.strip_h_lo + i);
+  }
+  if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, kTmemCols);
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) {
+      umma::mbar_init(l_full + i, kProducerGroup / 32);
+      umma::mbar_init(l_empty + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(h_empty + i, 1);
+      umma::mbar_init(acc_full + i, 1);
+      umma::mbar_init(acc_empty + i, 4);
+    }
+    *stored_count = 0;
+    tile_max[0] = tile_max[1] = tile_max[2] = 0u;
+  }
+  umma::fence_proxy_async_smem();
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // (see decimate2_tc_kernel)
+  pdl_launch_dependents();
+  const int total = p.tile_prefix[kDecStages];
+  int tile = dtc_first(p, total);
+  if (tile < total && !dtc_decode(p, tile).live) tile = dtc_next_live(p, tile, total);
+
+  if (warp < kProducers / 32) {
+    // ================================================================= producers
+    const int grp = warp >> 2, tg = tid & (kProducerGroup - 1);
+    float4 v[16];
+    unsigned stages_complete = 0;
+    const int slot0 = (tg & 3) * kRT + (tg >> 2);   // 16-byte units within a slice
+    DtcTile cur;
+    if (tile >= 0 && tile < total) {
+      cur = dtc_decode(p, tile);
+      dtc_deps_wait(p, cur, lane, stages_complete);
+      dth_load_slice<0>(cur, tg, 2 * grp, v);
+      dth_load_slice<1>(cur, tg, 2 * grp + 1, v);
+    }
+    for (int n = 0; tile >= 0 && tile < total; ++n) {
+      const int next = dtc_next_live(p, tile, total);
+      if ((warp & 3) == 0) DTC_STAMP(grp, n, 0);
+      // the tile's scale: 2^k brings its largest magnitude into [2^8, 2^9)
+      float mx = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+      const unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+      if (lane == 0) atomicMax(tile_max + n % 3, wmax);
+      asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");
+      int e = (int)(tile_max[n % 3] >> 23) - 127;      // floor(log2(max)); -127 for zero / subnormal tiles
+      int k = 8 - e;
+      k = k > 100 ? 100 : k;
+      const float scale = __uint_as_float((uint32_t)(k + 127) << 23);
+      if (tid == 0) {
+        tile_inv[n & 3] = __uint_as_float((uint32_t)(127 - k - kTapShift) << 23);
+        tile_max[(n + 2) % 3] = 0u;   // tile n - 1's slot: every producer read it before this barrier; next used by tile n + 2
+      }
+      // this A_hi buffer is free once the MMAs of tile n - 2 have completed
+      umma::mbar_wait(h_empty + (n & 1), ((n >> 1) & 1) ^ 1);
+      if ((warp & 3) == 0) DTC_STAMP(grp, n, 1);
+      uint4* hi_tile = reinterpret_cast<uint4*>(a_hi + (n & 1) * kTileBytes);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int sl = 2 * grp + j;
+        const int st = sl & 1;
+        if (sl >= 2) umma::mbar_wait(l_empty + sl - 2, n & 1);
+        else if (n > 0) umma::mbar_wait(l_empty + sl + 2, (n - 1) & 1);
+        if ((warp & 3) == 0) DTC_STAMP(grp, n, 2 + 2 * j);
+        uint4* hi = hi_tile + sl * (kSliceBytes / 16);
+        uint4* lo = reinterpret_cast<uint4*>(a_lo + st * kSliceBytes);
+#pragma unroll
+        for (int i = 0; i < kChunksPerThread; ++i) {
+          uint4 h, l;
+          dth_split8(v[8 * j + 2 * i], v[8 * j + 2 * i + 1], scale, h, l);
+          hi[slot0 + 32 * i] = h;
+          lo[slot0 + 32 * i] = l;
+        }
+        umma::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(l_full + sl);
+        if ((warp & 3) == 0) DTC_STAMP(grp, n, 3 + 2 * j);
+      }
+      if (next >= 0) {
+        cur = dtc_decode(p, next);
+        dtc_deps_wait(p, cur, lane, stages_complete);
+        if ((warp & 3) == 0) DTC_STAMP(grp, n, 6);
+        dth_load_slice<0>(cur, tg, 2 * grp, v);
+        dth_load_slice<1>(cur, tg, 2 * grp + 1, v);
+        if ((warp & 3) == 0) DTC_STAMP(grp, n, 7);
+      }
+      tile = next;
+    }
+  } else if (warp == kMmaWarp) {
+    // ================================================================= MMA issue
+    const uint32_t idesc = instr_desc_f16(kM, kN);
+    const uint64_t db_hi0 = umma::smem_desc(umma::smem_u32(t_hi), kStripRows * 16, 128) + (uint64_t)kStripRow0;
+    const uint64_t db_lo0 = umma::smem_desc(umma::smem_u32(t_lo), kStripRows * 16, 128) + (uint64_t)kStripRow0;
+    for (int n = 0; tile >= 0 && tile < total; ++n, tile = dtc_next_live(p, tile, total)) {
+      const int q = n & 1;
+      const uint32_t acc = tmem_base + (uint32_t)(q * kN);
+      const uint32_t hi_addr = umma::smem_u32(a_hi + q * kTileBytes);
+      DTC_STAMP(2, n, 0);
+      umma::mbar_wait(acc_empty + q, ((n >> 1) & 1) ^ 1);
+      umma::fence_after_thread_sync();
+      DTC_STAMP(2, n, 1);
+      for (int s = 0; s < kSlices; ++s) {     // cross terms first (see the accuracy note in the header)
+        const int st = s & 1;
+        umma::mbar_wait(l_full + s, n & 1);
+        umma::fence_after_thread_sync();
+        DTC_STAMP(2, n, 2 + s);
+        if (umma::elect_one_sync()) {
+          const uint64_t da_hi = umma::smem_desc(hi_addr + (uint32_t)(s * kSliceBytes), kRT * 16, 128);
+          const uint64_t da_lo = umma::smem_desc(umma::smem_u32(a_lo + st * kSliceBytes), kRT * 16, 128);
+#pragma unroll
+          for (int k = 0; k < kKStepsPerSlice; ++k) {
+            if (p.debug & 4) break;
+            const uint64_t a_off = (uint64_t)(2 * k * kRT);                    // 16-byte units: chunk columns 2 k, 2 k + 1
+            const uint64_t b_off = (uint64_t)(8 * (kKStepsPerSlice * s + k));  // strip row 56 - 8 gs
+            mma_f16(acc, da_lo + a_off, db_hi0 - b_off, idesc, (s | k) ? 1u : 0u);
+            mma_f16(acc, da_hi + a_off, db_lo0 - b_off, idesc, 1u);
+          }
+          umma::commit(l_empty + s);
+        }
+        __syncwarp();
+      }
+      if (umma::elect_one_sync()) {
+#pragma unroll
+        for (int gs = 0; gs < kSlices * kKStepsPerSlice; ++gs) {
+          if (p.debug & 4) break;
+          const int s = gs >> 1, k = gs & 1;
+          const uint64_t da_hi = umma::smem_desc(hi_addr + (uint32_t)(s * kSliceBytes), kRT * 16, 128);
+          mma_f16(acc, da_hi + (uint64_t)(2 * k * kRT), db_hi0 - (uint64_t)(8 * gs), idesc, 1u);
+        }
+        umma::commit(h_empty + q);
+        umma::commit(acc_full + q);
+      }
+      __syncwarp();
+      DTC_STAMP(2, n, 6);
+    }
+  } else if (warp < kPublishWarp) {
+    // ================================================================= epilogue (warps 8-11)
+    const int quad = warp - kEpilogueWarp0;
+    float* stg = epi_buf + quad * 32 * kEpiStride;
+    for (int n = 0; tile >= 0 && tile < total; ++n, tile = dtc_next_live(p, tile, total)) {
+      const int q = n & 1;
+      const DtcTile t = dtc_decode(p, tile);
+      if (quad == 0) DTC_STAMP(3, n, 0);
+      umma::mbar_wait(acc_full + q, (n >> 1) & 1);
+      umma::fence_after_thread_sync();
+      if (quad == 0) DTC_STAMP(3, n, 1);
+      const float inv = *reinterpret_cast<volatile float*>(tile_inv + (n & 3));
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(q * kN);
+#pragma unroll
+      for (int cq = 0; cq < kP / 16; ++cq) {
+        uint32_t r0[16], r1[16], r2[16], r3[16];
+        umma::tmem_ld_32x16_nowait(lane_base + 3 * kP + 16 * cq, r0);
+        umma::tmem_ld_32x16_nowait(lane_base + 2 * kP + 16 * cq, r1);
+        umma::tmem_ld_32x16_nowait(lane_base + 1 * kP + 16 * cq, r2);
+        umma::tmem_ld_32x16_nowait(lane_base + 16 * cq, r3);
+        umma::tmem_wait_ld();
+        float v0[16], v1[16], v2[16], v3[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          v0[c] = __uint_as_float(r0[c]), v1[c] = __uint_as_float(r1[c]), v2[c] = __uint_as_float(r2[c]), v3[c] = __uint_as_float(r3[c]);
+        if (cq == kP / 16 - 1) {
+          umma::fence_before_thread_sync();
+          __syncwarp();
+          if (lane == 0) umma::mbar_arrive(acc_empty + q);
+          if (quad == 0) DTC_STAMP(3, n, 2);
+        }
+        if (p.debug & 1) continue;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float s1 = __shfl_down_sync(0xffffffffu, v1[c], 1);
+          const float s2 = __shfl_down_sync(0xffffffffu, v2[c], 2);
+          const float s3 = __shfl_down_sync(0xffffffffu, v3[c], 3);
+          v0[c] = ((v0[c] + s1) + (s2 + s3)) * inv;
+        }
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+          *reinterpret_cast<float4*>(stg + lane * kEpiStride + 16 * cq + 4 * w) =
+              make_float4(v0[4 * w], v0[4 * w + 1], v0[4 * w + 2], v0[4 * w + 3]);
+      }
+      __syncwarp();
+      const int j_grp = (t.row0 + kGroupValid * quad) * kP;
+      for (int idx = lane; idx < kGroupValid * (kP / 4) && !(p.debug & 1); idx += 32) {
+        const int r = idx >> 4, c4 = idx & 15;
+        const int j = j_grp + r * kP + 4 * c4;
+        const float4 val = *reinterpret_cast<const float4*>(stg + r * kEpiStride + 4 * c4);
+        if (j + 4 <= t.len_out) {
+          *reinterpret_cast<float4*>(t.y + j) = val;
+        } else {
+          if (j < t.len_out) t.y[j] = val.x;
+          if (j + 1 < t.len_out) t.y[j + 1] = val.y;
+          if (j + 2 < t.len_out) t.y[j + 2] = val.z;
+        }
+      }
+      __syncwarp();
+      if (quad == 0) DTC_STAMP(3, n, 3);
+      if (lane == 0) {
+        __threadfence_block();
+        atomicAdd(stored_count, 1u);
+      }
+    }
+  } else if (warp == kPublishWarp) {
+    // ================================================================= publisher (see decimate2_tc_kernel)
+    int* stage_done = p.flags + (long long)kDecStages * p.batch * p.tiles_per_clip[0];
+    int n = 0;
+    for (int g = dtc_first(p, total); g < total; g = dtc_step(p, g, total)) {
+      const DtcTile t = dtc_decode(p, g);
+      if (lane == 0) {
+        if (t.live) {
+          ++n;
+          unsigned long long t0 = 0;
+          for (uint32_t spin = 0; *reinterpret_cast<volatile unsigned int*>(stored_count) < 4u * (unsigned)n; ++spin) {
+            __nanosleep(100);
+            if ((spin & 1023) == 1023) {
+              const unsigned long long now = umma::global_ns();
+              if (t0 == 0) t0 = now;
+              if (now - t0 > umma::kPollTimeoutNs) __trap();
+            }
+          }
+          __threadfence();
+          atomicAdd(dtc_flag(p, t.stage, t.clip, t.k), 4);
+        }
+        atomicAdd(stage_done + t.stage, 1);
+      }
+      __syncwarp();
+    }
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  AST_TIMELINE_STAMP_IF(warp == kMmaWarp && lane == 0, dec, blockIdx.x, 1);
+  if (warp == kMmaWarp) umma::tmem_dealloc(tmem_base, kTmemCols);
+  AST_TIMELINE_STAMP_IF(warp == kMmaWarp && lane == 0, dec, blockIdx.x, 3);
+}
+
+static int g_dec_half = 1;   // AST_DECIMATOR=tf32 selects the TF32-split kernel
+void set_decimator_half(int on) { g_dec_half = on; }
+
 int decimate_init() {
   AST_CUDA_TRY(cudaFuncSetAttribute(decimate2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dtc::kSmem));
+  AST_CUDA_TRY(cudaFuncSetAttribute(decimate2_tc_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dth::kSmem));
   return AST_OK;
 }
 
@@ -594,6 +943,24 @@ void host_decimator_strip(const double* taps_scaled, float* strip_hi, float* str
         memcpy(&lo, &lb, 4);
         strip_hi[(c * kStripRows + i) * 4 + e] = hi;
         strip_lo[(c * kStripRows + i) * 4 + e] = lo;
+      }
+}
+
+// host: the FP16-split kernel's strip images T[jj][kk] = 2^15 g[kk - 2 jj], jj = row - 248, kk = 8 c + e < 16, as
+// [chunk c][row][8 halves]: hi = FP16(value), lo = FP16(value - hi)
+int decimator_strip_h_bytes() { return dth::kStripBytes; }
+void host_decimator_strip_h(const double* taps_scaled, uint16_t* strip_hi, uint16_t* strip_lo) {
+  using namespace dth;
+  for (int c = 0; c < 2; ++c)
+    for (int i = 0; i < kStripRows; ++i)
+      for (int e = 0; e < 8; ++e) {
+        const int jj = i - (kStripRow0 + 3 * kP);   // row 248 <-> jj = 0
+        const int tap = 8 * c + e - 2 * jj;
+        const double g = (tap >= 0 && tap < kDecTaps) ? std::ldexp(taps_scaled[tap], kTapShift) : 0.0;
+        const __half hi = __float2half_rn((float)g);
+        const __half lo = __float2half_rn((float)(g - (double)__half2float(hi)));
+        memcpy(&strip_hi[(c * kStripRows + i) * 8 + e], &hi, 2);
+        memcpy(&strip_lo[(c * kStripRows + i) * 8 + e], &lo, 2);
       }
 }
 
@@ -646,6 +1013,8 @@ int launch_decimate_cascade_tc(const ast_plan* plan, const float* wave, const in
   p.flags = flags;
   p.strip_hi = plan->d_dec_strip_hi;
   p.strip_lo = plan->d_dec_strip_lo;
+  p.strip_h_hi = reinterpret_cast<const uint4*>(plan->d_dec_strip_h_hi);
+  p.strip_h_lo = reinterpret_cast<const uint4*>(plan->d_dec_strip_h_lo);
   {
     const char* env = getenv("AST_DEC_DEBUG");
     p.debug = env ? atoi(env) : 0;
@@ -671,7 +1040,10 @@ int launch_decimate_cascade_tc(const ast_plan* plan, const float* wave, const in
     }
   }
   ProfileSpan span("decimate2_tc_kernel", st);
-  AST_CUDA_TRY(launch_with_pdl(decimate2_tc_kernel, dim3((unsigned)ctas), dtc::kThreads, dtc::kSmem, st, p));
+  if (g_dec_half)
+    AST_CUDA_TRY(launch_with_pdl(decimate2_tc_h_kernel, dim3((unsigned)ctas), dtc::kThreads, dth::kSmem, st, p));
+  else
+    AST_CUDA_TRY(launch_with_pdl(decimate2_tc_kernel, dim3((unsigned)ctas), dtc::kThreads, dtc::kSmem, st, p));
   return AST_OK;
 }
 

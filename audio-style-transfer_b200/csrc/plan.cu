@@ -339,6 +339,10 @@ int ast_plan_create(const ast_config* cfg, ast_plan** out) {
     host_decimator_strip(taps_scaled.data(), strip_hi.data(), strip_lo.data());
     AST_ALLOC_COPY(p->d_dec_strip_hi, strip_hi.data(), sizeof(float) * strip_hi.size());
     AST_ALLOC_COPY(p->d_dec_strip_lo, strip_lo.data(), sizeof(float) * strip_lo.size());
+    std::vector<uint16_t> h_hi(decimator_strip_h_bytes() / 2), h_lo(decimator_strip_h_bytes() / 2);
+    host_decimator_strip_h(taps_scaled.data(), h_hi.data(), h_lo.data());
+    AST_ALLOC_COPY(p->d_dec_strip_h_hi, h_hi.data(), h_hi.size() * 2);
+    AST_ALLOC_COPY(p->d_dec_strip_h_lo, h_lo.data(), h_lo.size() * 2);
   }
 #undef AST_ALLOC_COPY
   int rc = upload_decimator_taps(taps_f.data());
@@ -349,8 +353,10 @@ int ast_plan_create(const ast_config* cfg, ast_plan** out) {
   if (const char* env = std::getenv("AST_OVERLAP")) set_overlap_streams(std::strcmp(env, "0") != 0);
   if (const char* env = std::getenv("AST_CQT"))  // diagnostic A/B switch: "fma" selects the FMA-pipe projection
     set_tc_cqt(std::strcmp(env, "fma") != 0);
-  if (const char* env = std::getenv("AST_DECIMATOR"))  // diagnostic A/B switch: "fma" selects the FMA-pipe kernel
+  if (const char* env = std::getenv("AST_DECIMATOR")) {  // diagnostic A/B switch: "fma" selects the FMA-pipe kernel, "tf32" the TF32-split tensor kernel
     set_tc_decimator(std::strcmp(env, "fma") != 0);
+    set_decimator_half(std::strcmp(env, "tf32") != 0);
+  }
   if (rc != AST_OK) {
     ast_plan_destroy(p);
     return rc;
@@ -372,6 +378,8 @@ int ast_plan_destroy(ast_plan* p) {
   cudaFree(p->d_cqt_tc_images);
   cudaFree(p->d_dec_strip_hi);
   cudaFree(p->d_dec_strip_lo);
+  cudaFree(p->d_dec_strip_h_hi);
+  cudaFree(p->d_dec_strip_h_lo);
   delete p;
   return AST_OK;
 }

@@ -32,6 +32,13 @@ constexpr int kAccStride = 516;   // float4 per warp of statistics accumulators 
 constexpr int kStftStatsIters = 64 / kStftWarps;   // statistics mode: 64 pairs = 128 frames per CTA tile
 constexpr size_t kStftSmem = sizeof(float2) * kStftWarps * kTileSize;
 constexpr size_t kStftStatsSmem = kStftSmem + sizeof(float4) * kStftWarps * kAccStride + sizeof(float) * kStftWarps;
+// AST_STFT_SMEM_PF: the samples of a warp's NEXT interior pair (1280 floats) are fetched by one cp.async.bulk into the
+// warp's own 5 KB buffer while it works on the current pair (feature mode; completion on a per-warp mbarrier)
+#ifndef AST_STFT_SMEM_PF
+#define AST_STFT_SMEM_PF 0
+#endif
+constexpr int kPfFloats = 40 * 32;   // one pair's window: frames 2p and 2p + 1
+constexpr size_t kStftFeatSmem = kStftSmem + (AST_STFT_SMEM_PF ? sizeof(float) * kStftWarps * kPfFloats + 8 * kStftWarps : 0);
 
 struct StftParams {
   const float* wave;
@@ -332,6 +339,32 @@ __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 3) 
   float n_acc = 0.f;
   if (kMode == 1)
     for (int k = lane; k < kAccStride; k += 32) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#if AST_STFT_SMEM_PF
+  float* pf = reinterpret_cast<float*>(stft_smem + kStftSmem) + warp * kPfFloats;
+  uint64_t* pf_bar = reinterpret_cast<uint64_t*>(stft_smem + kStftSmem + sizeof(float) * kStftWarps * kPfFloats) + warp;
+  const bool pf_ok = kMode == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  uint32_t pf_phase = 0;
+  bool pf_pending = false;
+  // interior pair (no reflection, both frames live): its 1280 samples are one contiguous, 1 KB-aligned run of the clip
+  auto pf_interior = [&](int pr) { return pr < p.pairs_per_clip && 2 * pr >= 2 && (2 * pr + 1) * kHop + kNfft / 2 <= len; };
+  auto pf_issue = [&](int pr) {
+    if (lane == 0) {
+      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(pf_bar), dst = (uint32_t)__cvta_generic_to_shared(pf);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(kPfFloats * 4)) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(x + 2 * pr * kHop - kNfft / 2), "r"((uint32_t)(kPfFloats * 4)), "r"(bar) : "memory");
+    }
+  };
+  if (pf_ok) {
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(pf_bar)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int first = blockIdx.x * p.iters * kStftWarps + warp;
+    if (p.iters > 0 && pf_interior(first)) pf_issue(first), pf_pending = true;
+  }
+#endif
 
   // Hann from the lane's rotation: w[32 i + lane] = 0.5 - 0.5 cos(2 pi i / 32 + theta), theta = 2 pi lane / 1024, expanded
   // with the compile-time cos / sin of 2 pi i / 32 against (cos theta, sin theta) = conj(W_1024^lane): two FFMA, no load
@@ -360,10 +393,29 @@ __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 3) 
         // interior: frame B sample n is frame A sample n + 256, x[base + 32 i], i = 0..39, feeds both
         const float* __restrict__ xp = x + base;
         float xv[40];
+#if AST_STFT_SMEM_PF
+        if (pf_pending) {
+          const uint32_t bar = (uint32_t)__cvta_generic_to_shared(pf_bar);
+          uint32_t done = 0;
+          while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(pf_phase) : "memory");
+          pf_phase ^= 1;
 #pragma unroll
-        for (int i = 0; i < 40; ++i) xv[i] = __ldg(xp + 32 * i);
+          for (int i = 0; i < 40; ++i) xv[i] = pf[32 * i + lane];
+          __syncwarp();   // every lane has its samples: the buffer may be refilled
+          pf_pending = false;
+        } else
+#endif
+        {
+#pragma unroll
+          for (int i = 0; i < 40; ++i) xv[i] = __ldg(xp + 32 * i);
+        }
+#if AST_STFT_SMEM_PF
+        if (pf_ok && it + 1 < p.iters && pf_interior(pair + kStftWarps)) pf_issue(pair + kStftWarps), pf_pending = true;
+#endif
 #ifndef AST_STFT_PF
-#define AST_STFT_PF 1
+#define AST_STFT_PF (AST_STFT_SMEM_PF ? 0 : 1)
 #endif
 #if AST_STFT_PF == 1
         // this warp's next pair starts kStftWarps x 512 samples further; its first 768 samples are being read by the
@@ -564,12 +616,12 @@ __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 3) 
 static int g_stft_ctas_per_sm = AST_STFT_CTAS;
 
 int stft_init() {
-  AST_CUDA_TRY(cudaFuncSetAttribute(stft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStftSmem));
+  AST_CUDA_TRY(cudaFuncSetAttribute(stft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStftFeatSmem));
   if (const char* env = getenv("AST_STFT_CARVEOUT"))   // diagnostic: shared-memory share of the unified L1 / shared array, %
     AST_CUDA_TRY(cudaFuncSetAttribute(stft_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(env)));
   AST_CUDA_TRY(cudaFuncSetAttribute(stft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStftStatsSmem));
   int n = 0;
-  AST_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stft_kernel<0>, kStftThreads, kStftSmem));
+  AST_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stft_kernel<0>, kStftThreads, kStftFeatSmem));
   g_stft_ctas_per_sm = n > 0 ? n : 1;
   return AST_OK;
 }
@@ -645,9 +697,9 @@ int launch_stft(const ast_plan* plan, const float* wave, const int32_t* lengths,
   } else if (pdl) {
     // programmatic dependent of the CQT projection launched just before it on the same stream: the kernel never
     // waits for it (disjoint output columns), so its CTAs fill the SMs as the persistent CQT CTAs retire
-    AST_CUDA_TRY(launch_with_pdl(stft_kernel<0>, grid, kStftThreads, kStftSmem, st, p));
+    AST_CUDA_TRY(launch_with_pdl(stft_kernel<0>, grid, kStftThreads, kStftFeatSmem, st, p));
   } else {
-    stft_kernel<0><<<grid, kStftThreads, kStftSmem, st>>>(p);
+    stft_kernel<0><<<grid, kStftThreads, kStftFeatSmem, st>>>(p);
     AST_LAUNCH_CHECK("stft_kernel");
   }
   return AST_OK;
