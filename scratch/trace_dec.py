@@ -4,7 +4,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 b = importlib.import_module("audio_style_transfer_b200.build")
-out = os.path.join(ROOT, "scratch", "libast_trace.so")
+out = os.environ.get("TRACE_LIB", os.path.join(ROOT, "scratch", "libast_trace.so"))
 if "--build" in sys.argv or not os.path.exists(out):
     cmd = [b._nvcc()] + b.NVCC_FLAGS + ["-DAST_TRACE", "-o", out] + [os.path.join(b.CSRC, s) for s in b.SOURCES]
     subprocess.check_call(cmd)
