@@ -595,7 +595,7 @@ constexpr int kStripRow0 = 56;                 // strip row of (n = 0, gs = 0): 
 constexpr int kStripBytes = 2 * kStripRows * 16;
 constexpr int kTapShift = 15;                  // taps are staged as g * 2^15 (largest tap ~ 0.65)
 constexpr int kChunksPerThread = kM * kSliceChunks / kProducerGroup;   // 4 shared-memory chunks (8 samples each) per slice
-constexpr size_t kSmem = 2 * kTileBytes + 2 * kSliceBytes + 2 * kStripBytes + sizeof(float) * kEpiFloats + 256 + 128 * 64;   // + the tile table
+constexpr size_t kSmem = 4 * kTileBytes + 2 * kStripBytes + sizeof(float) * kEpiFloats + 256 + 128 * 64;   // + the tile table
 }  // namespace dth
 
 __host__ __device__ constexpr uint32_t instr_desc_f16(int m, int n) {   // kind::f16, A = B = FP16, FP32 accumulate, K-major
@@ -659,40 +659,40 @@ struct DthWalk {
   }
 };
 
-// One 32-sample slice of a tile for a producer thread: shared-memory chunk cc = tg & 3 (samples 8 cc .. 8 cc + 7 of the
-// slice) of the four rows rho = (tg >> 2) + 32 i, i.e. lane row tg >> 2 of row group i.  v[8 J + 2 i + h]: half h of it.
+// One 32-sample slice of a tile for a producer thread: 16 bytes (four samples, f = tg & 7) of the eight rows
+// rho = (tg >> 3) + 16 i - eight lanes cover a row's 128 contiguous bytes, whole sectors (a thread that loads the two halves
+// of a shared-memory chunk in two instructions requests every sector twice: .cg loads are not kept in the L1).
+// v[8 J + i]: row i of the group's J-th slice.
 template <int J>
 __device__ __forceinline__ void dth_load_slice(const DtcTile& t, int tg, int s, float4 (&v)[16]) {
   using namespace dth;
-  const int a0 = kRS * (t.row0 + (tg >> 2)) - kDecHalf + 32 * s + 8 * (tg & 3);
+  const int a0 = kRS * (t.row0 + (tg >> 3)) - kDecHalf + 32 * s + 4 * (tg & 7);
   if (t.debug & 2) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[8 * J + i] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
 #pragma unroll
-  for (int i = 0; i < kChunksPerThread; ++i) {
-    const int a = a0 + kRS * kGroupValid * i;
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-      v[8 * J + 2 * i + h] = t.interior ? ld_cg_f4(t.x + a + 4 * h) : dtc_load4(t.x, a + 4 * h, t.len_in, t.vec_ok);
+  for (int i = 0; i < 8; ++i) {
+    const int a = a0 + kRS * (kGroupValid * (i >> 1) + 16 * (i & 1));
+    v[8 * J + i] = t.interior ? ld_cg_f4(t.x + a) : dtc_load4(t.x, a, t.len_in, t.vec_ok);
   }
 }
 
-// 8 samples x scale -> FP16 hi and FP16 residual images (one 16-byte chunk each)
-__device__ __forceinline__ void dth_split8(const float4& a, const float4& b, float scale, uint4& hi, uint4& lo) {
-  const float x[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
-  uint32_t h[4], l[4];
+// 4 samples x scale -> FP16 hi and FP16 residual images (half a 16-byte chunk each)
+__device__ __forceinline__ void dth_split4(const float4& a, float scale, uint2& hi, uint2& lo) {
+  const float x[4] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale};
+  uint32_t h[2], l[2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 2; ++i) {
     const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
     const float2 back = __half22float2(hh);
     const __half2 ll = __floats2half2_rn(x[2 * i] - back.x, x[2 * i + 1] - back.y);
     h[i] = *reinterpret_cast<const uint32_t*>(&hh);
     l[i] = *reinterpret_cast<const uint32_t*>(&ll);
   }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
+  hi = make_uint2(h[0], h[1]);
+  lo = make_uint2(l[0], l[1]);
 }
 
 __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_h_kernel(const DecimateTcParams p) {
@@ -700,13 +700,15 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_h_kernel(const 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   AST_TIMELINE_STAMP(dec, blockIdx.x, 0);
   unsigned char* a_hi = smem_raw;                            // [2 tiles][4 slices][4 chunk columns][130 rows][8 halves]
-  unsigned char* a_lo = a_hi + 2 * kTileBytes;               // [2 stages][4][130][8]
-  unsigned char* t_hi = a_lo + 2 * kSliceBytes;
+  unsigned char* a_lo = a_hi + 2 * kTileBytes;               // the residual image, same shape: with 227 KB per SM there is
+  unsigned char* t_hi = a_lo + 2 * kTileBytes;               // room for whole tiles, so no producer waits for the cross-term MMAs
   unsigned char* t_lo = t_hi + kStripBytes;
   float* epi_buf = reinterpret_cast<float*>(t_lo + kStripBytes);   // [4 warps][32 rows][68] epilogue transpose
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + kEpiFloats);
-  uint64_t* l_full = bars;          // (the barrier set of decimate2_tc_kernel)
-  uint64_t* l_empty = bars + 4;
+  // l_full[tile parity][slice]: the producers are held back by h_empty only (MMAs of tile n - 2 done), so they may arrive
+  // for tile n + 1 before the MMA warp has waited for tile n: one barrier set per tile parity keeps every barrier at most
+  // one phase ahead of its waiter
+  uint64_t* l_full = bars;          // [2][4] producers -> MMA: slice staged (both images written); 4 warp arrivals
   uint64_t* h_empty = bars + 8;
   uint64_t* acc_full = bars + 10;
   uint64_t* acc_empty = bars + 12;
@@ -729,7 +731,7 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_h_kernel(const 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) {
       umma::mbar_init(l_full + i, kProducerGroup / 32);
-      umma::mbar_init(l_empty + i, 1);
+      umma::mbar_init(l_full + 4 + i, kProducerGroup / 32);
     }
     for (int i = 0; i < 2; ++i) {
       umma::mbar_init(h_empty + i, 1);
@@ -754,7 +756,9 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_h_kernel(const 
     const int grp = warp >> 2, tg = tid & (kProducerGroup - 1);
     float4 v[16];
     unsigned stages_complete = 0;
-    const int slot0 = (tg & 3) * kRT + (tg >> 2);   // 16-byte units within a slice
+    // 8-byte units within a slice: half (tg & 1) of chunk column (tg & 7) >> 1, row tg >> 3 (+ 16 i); with kRT = 2 mod 8
+    // the 64-bit stores of a half-warp (8 pieces x 2 rows) fall into 32 different banks
+    const int slot0 = 2 * (((tg & 7) >> 1) * kRT + (tg >> 3)) + (tg & 1);
     DtcTile cur;
     if (tile < total) {
       cur = walk.get(tile);
@@ -787,22 +791,19 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_h_kernel(const 
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int sl = 2 * grp + j;
-        const int st = sl & 1;
-        if (sl >= 2) umma::mbar_wait(l_empty + sl - 2, n & 1);
-        else if (n > 0) umma::mbar_wait(l_empty + sl + 2, (n - 1) & 1);
         if ((warp & 3) == 0) DTC_STAMP(grp, n, 2 + 2 * j);
-        uint4* hi = hi_tile + sl * (kSliceBytes / 16);
-        uint4* lo = reinterpret_cast<uint4*>(a_lo + st * kSliceBytes);
+        uint2* hi = reinterpret_cast<uint2*>(hi_tile + sl * (kSliceBytes / 16));
+        uint2* lo = reinterpret_cast<uint2*>(a_lo + (n & 1) * kTileBytes + sl * kSliceBytes);
 #pragma unroll
-        for (int i = 0; i < kChunksPerThread; ++i) {
-          uint4 h, l;
-          dth_split8(v[8 * j + 2 * i], v[8 * j + 2 * i + 1], scale, h, l);
-          hi[slot0 + 32 * i] = h;
+        for (int i = 0; i < 8; ++i) {
+          uint2 h, l;
+          dth_split4(v[8 * j + i], scale, h, l);
+          hi[slot0 + 32 * i] = h;   // row + 16 i: 32 eight-byte units further
           lo[slot0 + 32 * i] = l;
         }
         umma::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) umma::mbar_arrive(l_full + sl);
+        if (lane == 0) umma::mbar_arrive(l_full + 4 * (n & 1) + sl);
         if ((warp & 3) == 0) DTC_STAMP(grp, n, 3 + 2 * j);
       }
       if (next < total) {
@@ -812,22 +813,6 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_h_kernel(const 
         dth_load_slice<0>(cur, tg, 2 * grp, v);
         dth_load_slice<1>(cur, tg, 2 * grp + 1, v);
         if ((warp & 3) == 0) DTC_STAMP(grp, n, 7);
-        // stage 0 reads the waveform from DRAM: the tile after this one is requested into the L2 now (its 119 rows are
-        // one contiguous run; four lanes take a quarter each), so that its loads, one tile from now, find it there
-        if (warp == 0 && lane < 4 && !(p.debug & 16)) {
-          const int nn = walk.next_live(next + 1);
-          if (nn < total) {
-            const DtcTile t2 = walk.get(nn);
-            if (t2.stage == 0 && t2.vec_ok) {
-              int lo = kRS * t2.row0 - kDecHalf, hi = kRS * (t2.row0 + kGroupValid * (kGroups - 1) + 32) - kDecHalf;
-              lo = lo < 0 ? 0 : lo;
-              hi = (hi > t2.len_in ? t2.len_in : hi) & ~3;
-              const int quarter = ((hi - lo + 15) / 16) * 4;   // floats, a multiple of 4
-              const int a = lo + lane * quarter, e = a + quarter < hi ? a + quarter : hi;
-              if (e > a) umma::prefetch_l2_bulk(t2.x + a, (uint32_t)(e - a) * 4u);
-            }
-          }
-        }
       }
       tile = next;
     }
@@ -845,13 +830,12 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_h_kernel(const 
       umma::fence_after_thread_sync();
       DTC_STAMP(2, n, 1);
       for (int s = 0; s < kSlices; ++s) {     // cross terms first (see the accuracy note in the header)
-        const int st = s & 1;
-        umma::mbar_wait(l_full + s, n & 1);
+        umma::mbar_wait(l_full + 4 * q + s, (n >> 1) & 1);
         umma::fence_after_thread_sync();
         DTC_STAMP(2, n, 2 + s);
         if (umma::elect_one_sync()) {
           const uint64_t da_hi = umma::smem_desc(hi_addr + (uint32_t)(s * kSliceBytes), kRT * 16, 128);
-          const uint64_t da_lo = umma::smem_desc(umma::smem_u32(a_lo + st * kSliceBytes), kRT * 16, 128);
+          const uint64_t da_lo = umma::smem_desc(umma::smem_u32(a_lo + q * kTileBytes + s * kSliceBytes), kRT * 16, 128);
 #pragma unroll
           for (int k = 0; k < kKStepsPerSlice; ++k) {
             if (p.debug & 4) break;
@@ -860,7 +844,6 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_h_kernel(const 
             mma_f16(acc, da_lo + a_off, db_hi0 - b_off, idesc, (s | k) ? 1u : 0u);
             mma_f16(acc, da_hi + a_off, db_lo0 - b_off, idesc, 1u);
           }
-          umma::commit(l_empty + s);
         }
         __syncwarp();
       }
@@ -872,7 +855,7 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_h_kernel(const 
           const uint64_t da_hi = umma::smem_desc(hi_addr + (uint32_t)(s * kSliceBytes), kRT * 16, 128);
           mma_f16(acc, da_hi + (uint64_t)(2 * k * kRT), db_hi0 - (uint64_t)(8 * gs), idesc, 1u);
         }
-        umma::commit(h_empty + q);
+        umma::commit(h_empty + q);    // both images of this tile's buffer may be refilled
         umma::commit(acc_full + q);
       }
       __syncwarp();
@@ -965,6 +948,8 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_h_kernel(const 
     // ================================================================= publisher (see decimate2_tc_kernel)
     int* stage_done = p.flags + (long long)kDecStages * p.batch * p.tiles_per_clip[0];
     int n = 0;
+    // (An L2 prefetch of the stage-0 tiles two to four tiles ahead - cp.async.bulk.prefetch.L2 issued from the producers or
+    // from this warp - was measured: no gain, 0.0900 vs 0.0892 ms.)
     for (int g = 0; g < total; ++g) {
       const DtcTile t = walk.get(g);
       if (t.live) {   // every epilogue warp has released its rows of the CTA's n-th live tile (one counter per warp:
