@@ -1109,7 +1109,7 @@ int launch_decimate_cascade_tc(const ast_plan* plan, const float* wave, const in
   {
     // measured at 64 clips (scratch/tail_sweep.sh, FP16 kernel): off 0.2834 ms per feature step, 64 CTAs 0.2800, 48 0.2774,
     // 32 (two clips per CTA) 0.2750, 24 0.2738 but a slower statistics call (0.303 vs 0.293 ms), 16 0.2850
-    int want = 32, clips_per_cta = 2;
+    int want = g_dec_half ? 32 : 64, clips_per_cta = g_dec_half ? 2 : 1;   // (the TF32 kernel's longer levels: 64 CTAs, 0.2980 vs 0.3015 ms)
     if (const char* env = getenv("AST_DEC_TAIL_CTAS")) want = atoi(env), clips_per_cta = 16;   // diagnostic sweep
     int first_chain = kDecStages;
     while (first_chain > 0 && p.tiles_per_clip[first_chain - 1] <= 2) --first_chain;
