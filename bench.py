@@ -55,7 +55,7 @@ KERNEL_BYTES_PER_CLIP = {  # compulsory input + output bytes of each kernel as t
     "cqt_tc_kernel": sum(_OCT) * 4 + BYTES_SECTIONS_CQT,
     "istft_kernel": BYTES_ISTFT_PATH,
 }
-# dense FLOPs per clip the two tensor-core kernels issue (TF32 split terms and padded tiles included)
+# dense FLOPs per clip the two tensor-core kernels issue (the three split terms and padded tiles included)
 _DEC_TILES = [-(-(-(-n // 64)) // 116) for n in _OCT[1:]]               # 116 rows of 64 outputs per tile: 15, 8, 4, 2, 1, 1
 TENSOR_FLOPS_PER_CLIP = {
     "decimate2_tc_kernel": 2.0 * 3 * 128 * 256 * 128 * sum(_DEC_TILES),         # M128 N256 K128 x 3 terms, 31 tiles per clip
@@ -567,9 +567,14 @@ def main():
                          "achieved_gbs": nbytes / (avg * 1e-3) / 1e9 if avg > 0 else None}
         if name in TENSOR_FLOPS_PER_CLIP and avg > 0:
             tf = TENSOR_FLOPS_PER_CLIP[name] * CLIPS_PER_GPU / (avg * 1e-3) / 1e12
-            kernels[name]["tensor_tflops_tf32_issued"] = tf
+            # the decimator's default kernel splits its operands into FP16 pairs (kind::f16, K = 16 per MMA: the same
+            # issued FLOPs at twice the TF32 rate); AST_DECIMATOR=tf32 selects the TF32-split kernel
+            half = name == "decimate2_tc_kernel" and os.environ.get("AST_DECIMATOR", "f16") not in ("tf32", "fma")
+            kind = "f16" if half else "tf32"
+            kernels[name]["tensor_kind"] = kind
+            kernels[name]["tensor_tflops_%s_issued" % kind] = tf
             if tf32_peak:
-                kernels[name]["tensor_frac_of_tf32_peak"] = tf / tf32_peak
+                kernels[name]["tensor_frac_of_%s_peak" % kind] = tf / (2 * tf32_peak if half else tf32_peak)
         if name != "istft_kernel":
             feature_ms += tot / args.steps
     feat_kernels = {k: v for k, v in kernels.items() if k != "istft_kernel"}

@@ -556,10 +556,11 @@ def test_features_host_full_size_chunks_repeatedly(fe, piano_stats):
 
 
 @pytest.mark.parametrize("env", [{"AST_DECIMATOR": "fma"}, {"AST_CQT": "fma"}, {"AST_DECIMATOR": "fma", "AST_CQT": "fma"},
-                                 {"AST_OVERLAP": "0"}, {"AST_CQT_TMA": "0"}])
+                                 {"AST_OVERLAP": "0"}, {"AST_CQT_TMA": "0"}, {"AST_DECIMATOR": "tf32"}])
 def test_diagnostic_kernel_variants_agree(fe, tmp_path, env):
-    """The FMA-pipe twins of the two tensor-core kernels (AST_DECIMATOR=fma, AST_CQT=fma) and the serial launch order
-    (AST_OVERLAP=0) are diagnostics of the same library, selected when a plan is created: run them in a fresh process
+    """The FMA-pipe twins of the two tensor-core kernels (AST_DECIMATOR=fma, AST_CQT=fma), the TF32-split decimator
+    (AST_DECIMATOR=tf32; the default splits into FP16 pairs) and the serial launch order (AST_OVERLAP=0) are diagnostics
+    of the same library, selected when a plan is created: run them in a fresh process
     and compare with the default path (and so, transitively, with the oracle)."""
     import os
     import subprocess
@@ -582,3 +583,23 @@ def test_diagnostic_kernel_variants_agree(fe, tmp_path, env):
     assert got.shape == ref.shape
     assert np.array_equal(got[..., :513], ref[..., :513])                       # the STFT does not depend on the switches
     assert np.abs(got[..., 513:] - ref[..., 513:]).max() <= 1e-5 * np.abs(ref[..., 513:]).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gain", [2.0 ** -30, 1e-4, 37.0, 3.0e4, 2.0 ** 40])
+def test_cqt_is_homogeneous_over_the_float_range(fe, gain):
+    """The decimator stages its operands as FP16 pairs scaled PER TILE by a power of two taken from the tile's own largest
+    magnitude, so the result must not depend on the input's scale: CQT(g x) = g CQT(x) for gains far outside FP16's range
+    (a fixed scale would overflow at |x| > 65504 / 2^k and flush small signals to zero).  The clip has a loud and a
+    40 dB quieter half, so one clip holds tiles of very different scales too.  librosa's CQT (utilityFunctions.py:52) is
+    linear; the tolerance is the CQT parity tolerance."""
+    wave = synth.clip("violin", 77, 60000).copy()
+    wave[30000:] *= 0.01
+    base = fe.cqt(cuda(wave[None]))[0].cpu().numpy().astype(np.float64)
+    scaled = (wave.astype(np.float64) * gain).astype(np.float32)
+    got = fe.cqt(cuda(scaled[None]))[0].cpu().numpy().astype(np.float64) / gain
+    assert np.isfinite(got).all()
+    assert np.abs(got - base).max() <= 1e-5 * np.abs(base).max()
+    # the quiet half on its own terms: relative to ITS largest value (frames well inside it)
+    q0 = 30000 // 256 + 40   # (the lowest octave's filters span 64 frames)
+    assert np.abs(got[:, q0:] - base[:, q0:]).max() <= 2e-5 * np.abs(base[:, q0:]).max()
