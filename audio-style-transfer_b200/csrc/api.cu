@@ -38,6 +38,8 @@ void profile_mark(const char* name, cudaStream_t st, bool begin) {
 
 static int g_overlap_streams = 1;  // AST_OVERLAP=0: plain launch order STFT, decimator, CQT (no programmatic overlap of the STFT)
 void set_overlap_streams(int on) { g_overlap_streams = on; }
+static int g_stft_second = 1;   // AST_FEATURE_ORDER=dcs: round 2's earlier order decimator -> CQT -> STFT
+void set_stft_second(int on) { g_stft_second = on; }
 
 static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
@@ -236,9 +238,22 @@ int ast_features_forward(const ast_plan* plan, const float* wave, const int32_t*
   // operation, so nothing of this call starts before the previous call's kernels have finished.
   rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, st,
                                /*flags_zeroed=*/chained);
-  if (rc == AST_OK)
-    rc = launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride,
-                    use_tc_decimator() ? w.dec_flags : nullptr, oq, st);
+  if (rc != AST_OK) return rc;
+  if (chained && g_stft_second) {
+    // decimator -> STFT -> CQT projection.  The FP16-split decimator leaves 16 K registers and 35 KB of shared memory
+    // of every SM free: exactly one 4-warp STFT CTA, so the STFT starts UNDER the decimator (tensor pipe there, FP32 / LSU
+    // pipes here), takes the SMs over as the decimator's CTAs retire, and the CQT projection's persistent CTAs (a whole SM
+    // each) start as the STFT's last wave drains.  The STFT's last CTA waits for its programmatic primary (now the
+    // decimator), every CQT CTA for its primary (now the STFT) before it exits: "the call's last kernel is complete"
+    // still means the whole call is.
+    rc = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st, 0, /*pdl=*/true,
+                     reinterpret_cast<unsigned int*>(w.dec_flags + tail_counter_index(batch, max_samples)), stat4, stat4_stride);
+    if (rc != AST_OK) return rc;
+    return launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, oq, st,
+                      /*tile_queue=*/true);
+  }
+  rc = launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride,
+                  use_tc_decimator() ? w.dec_flags : nullptr, oq, st);
   if (rc != AST_OK) return rc;
   // the STFT never waits for the CQT projection it is a programmatic dependent of, so it could finish first; its last
   // CTA to finish then waits for that grid (tail counter), so that "the call's last kernel is complete" means the whole
@@ -319,13 +334,23 @@ int ast_stats_accumulate(const ast_plan* plan, const float* wave, const int32_t*
   oq.f_off = kFStft;
   oq.stats_off = kFStft;
   oq.cqt_part = sc.part_cqt;
-  rc = launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride,
-                  use_tc_decimator() ? w.dec_flags : nullptr, oq, st);
-  if (rc != AST_OK) return rc;
   const bool chained = g_overlap_streams && !profile_on() && use_tc_decimator();
-  rc = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st, 0, /*pdl=*/chained, nullptr, nullptr, 0,
-                   sc.part_stft, sc.part_n);
-  if (rc != AST_OK) return rc;
+  if (chained && g_stft_second && !getenv("AST_STATS_ORDER_DCS")) {
+    // as in the feature call: decimator -> STFT (statistics mode) -> CQT projection drawing its tiles from the queue
+    rc = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st, 0, /*pdl=*/true, nullptr, nullptr, 0,
+                     sc.part_stft, sc.part_n);
+    if (rc != AST_OK) return rc;
+    rc = launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, oq, st,
+                    /*tile_queue=*/true);
+    if (rc != AST_OK) return rc;
+  } else {
+    rc = launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride,
+                    use_tc_decimator() ? w.dec_flags : nullptr, oq, st);
+    if (rc != AST_OK) return rc;
+    rc = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st, 0, /*pdl=*/chained, nullptr, nullptr, 0,
+                     sc.part_stft, sc.part_n);
+    if (rc != AST_OK) return rc;
+  }
   rc = launch_stats_finalize_clips(sc.part_stft, sc.part_n, stft_tiles, sc.part_cqt, stats_cqt_tiles(max_samples), lengths,
                                    max_samples, batch, sc.clip_stats, st);
   if (rc != AST_OK) return rc;

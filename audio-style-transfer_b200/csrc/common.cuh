@@ -225,7 +225,7 @@ int launch_decimate_cascade(const ast_plan* plan, const float* wave, const int32
                             int* flags, cudaStream_t st, bool flags_zeroed = false);
 int launch_cqt(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
                long long wave_stride, const float* ws, long long ws_clip_stride, const int* dec_flags, const OutSpec& out,
-               cudaStream_t st);
+               cudaStream_t st, bool tile_queue = false);
 int launch_istft(const ast_plan* plan, const float* spec, int batch, int dim1, int f_in, int layout, int window,
                  int overlap, int n_frames, float* wave_out, long long out_stride, cudaStream_t st);
 int launch_clip_stats(const float* feats, const int32_t* n_frames, int batch, int t_dim, int f_dim, double* clip_stats,
@@ -240,7 +240,7 @@ int cqt_tc_image_floats();
 void host_cqt_tc_images(const double* kmat_256x24, float* images);
 int launch_cqt_tc(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
                   long long wave_stride, const float* ws, long long ws_clip_stride, const int* dec_flags, const OutSpec& out,
-                  cudaStream_t st);
+                  cudaStream_t st, bool tile_queue = false);
 void set_tc_cqt(int on);
 void set_overlap_streams(int on);
 bool use_tc_cqt();
@@ -249,6 +249,7 @@ void host_decimator_strip(const double* taps_scaled, float* strip_hi, float* str
 int decimator_strip_h_bytes();
 void host_decimator_strip_h(const double* taps_scaled, uint16_t* strip_hi, uint16_t* strip_lo);  // decimator_strip_h_bytes() each
 void set_decimator_half(int on);
+void set_stft_second(int on);
 size_t decimator_flag_bytes(int batch, long long max_samples);
 int decimator_tile_outputs();                       // outputs per decimator tile (7424)
 int decimator_tiles_stage0(long long max_samples);  // tiles per clip of the first stage = row stride of the flag array

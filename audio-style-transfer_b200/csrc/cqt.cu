@@ -119,9 +119,9 @@ bool use_tc_cqt() { return g_use_tc_cqt != 0; }
 
 int launch_cqt(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
                long long wave_stride, const float* ws, long long ws_clip_stride, const int* dec_flags, const OutSpec& out,
-               cudaStream_t st) {
+               cudaStream_t st, bool tile_queue) {
   if (g_use_tc_cqt || out.cqt_part)   // (the statistics epilogue exists in the tensor-core kernel only)
-    return launch_cqt_tc(plan, wave, lengths, batch, max_samples, wave_stride, ws, ws_clip_stride, dec_flags, out, st);
+    return launch_cqt_tc(plan, wave, lengths, batch, max_samples, wave_stride, ws, ws_clip_stride, dec_flags, out, st, tile_queue);
   CqtParams p;
   p.wave = wave;
   p.wave_stride = wave_stride;

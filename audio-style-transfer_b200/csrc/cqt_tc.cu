@@ -93,8 +93,8 @@ constexpr int kTmemCols = 256;
 constexpr int kStage = (kMaxBlockChunks + kGroupThreads - 1) / kGroupThreads;  // 12 chunks per producer thread per block at most
 constexpr int kEpiStride = 25;            // floats per staged row (24 values + 1: conflict-free row-per-lane writes)
 constexpr int kEpiFloats = 8 * 32 * kEpiStride;  // one [32 rows][25] transpose buffer per epilogue warp
-constexpr size_t kSmem = sizeof(float) * (kStages * kStageFloats + kBFloats + kEpiFloats) + 256 + 1024;   // + alignment slack
-constexpr size_t kSmemTma = sizeof(float) * (kStagesTma * kStageFloats + kBFloats + kEpiFloats / 2 * kEpiGroupsTma) + 256 + 1024;
+constexpr size_t kSmem = sizeof(float) * (kStages * kStageFloats + kBFloats + kEpiFloats) + 512 + 1024;   // barriers + tile ring, alignment slack
+constexpr size_t kSmemTma = sizeof(float) * (kStagesTma * kStageFloats + kBFloats + kEpiFloats / 2 * kEpiGroupsTma) + 512 + 1024;
 
 // rows per chunk column of an octave's blocks: 128 frames + window / hop - 1 shifts, rounded up to a multiple of 8
 // (chunk columns are TMA destinations: 128-byte aligned)
@@ -130,6 +130,7 @@ struct CqtTcParams {
   const int* flags;    // the decimator's per-tile completion counters ([stage][clip][tile], 4 = done) or nullptr
   int flag_tiles0;     // tiles per clip of decimator stage 0 (row stride of the counters)
   const int* stage_done;          // finished-tile counter per decimator stage
+  int* queue;                     // TMA path: the launch's next unassigned tile (zeroed with the counters), or nullptr: tiles dealt round-robin
   int stage_tiles[kOctaves - 1];  // tiles of each stage (all clips): stage_done[s] == stage_tiles[s] <=> stage complete
   int dec_tile_outputs;
   int debug;   // diagnostic bit mask (AST_CQT_DEBUG): 1 no epilogue stores, 2 no producer loads, 4 no MMAs, 8 no L2 prefetch
@@ -297,6 +298,59 @@ __device__ __noinline__ void issue_block_any(int oct, uint32_t a_hi_addr, uint32
   }
 }
 
+// The CTA's k-th tile.  Round-robin (tile = CTA + k grid) makes every CTA's work equal, but the persistent CTAs of this
+// kernel do not start together - each needs a whole SM and gets it when the kernel before it leaves one (the feature
+// call's STFT drains over ~ 30 us) - so equal lists end as staggered as they start.  With a queue the TMA thread draws
+// the next tile number from a global counter (tiles are numbered heaviest octave first) and publishes it in a small
+// shared-memory ring the other roles read; total marks the end.
+constexpr int kTileRing = 32;   // entries; the TMA thread is at most ~ 7 tiles ahead of the epilogue (4 stages + 2 accumulator sets)
+struct TileSeq {
+  volatile int* ring;   // [kTileRing] tiles, [kTileRing] = number of entries published
+  int total;
+  bool dynamic;
+  __device__ __forceinline__ int get(int k) const {
+    if (!dynamic) {
+      const long long t = (long long)blockIdx.x + (long long)k * gridDim.x;
+      return t < total ? (int)t : total;
+    }
+    while (ring[kTileRing] <= k) __nanosleep(20);
+    return ring[k & (kTileRing - 1)];
+  }
+};
+struct TileFetcher {   // the TMA thread only
+  TileSeq seq;
+  int* queue;
+  int fetched;
+  bool ended;
+  int n_epi;   // epilogue warps: ring[kTileRing + 1 + w] = positions warp w has read
+  __device__ __forceinline__ void ensure(int upto) {   // entries 0 .. upto are published (or the end marker is)
+    while (seq.dynamic && fetched <= upto && !ended) {
+      // Dead tiles (ragged batch) cost this thread nothing but the epilogue a tile of zero rows, so it could run any
+      // distance ahead: an entry is overwritten only when every epilogue warp - the last readers - is past it.  (The
+      // epilogue never waits for a tile this thread has not issued yet: it is behind, so this cannot deadlock.)
+      for (;;) {
+        int slowest = fetched;
+        for (int w = 0; w < n_epi; ++w) {
+          const int r = seq.ring[kTileRing + 1 + w];
+          slowest = r < slowest ? r : slowest;
+        }
+        if (fetched - slowest < kTileRing - 1) break;
+        __nanosleep(100);
+      }
+      int t = atomicAdd(queue, 1);
+      if (t >= seq.total) t = seq.total, ended = true;
+      seq.ring[fetched & (kTileRing - 1)] = t;
+      __threadfence_block();
+      seq.ring[kTileRing] = ++fetched;
+    }
+  }
+  __device__ __forceinline__ int peek(int k) {   // tile k if there is one, else total
+    if (!seq.dynamic) return seq.get(k);
+    ensure(k);
+    return k < fetched ? seq.ring[k & (kTileRing - 1)] : seq.total;
+  }
+};
+
 AST_TIMELINE_DEFINE(cqt)
 
 template <bool kTma>
@@ -321,6 +375,7 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
   uint64_t* acc_empty = bars + 10;  // [2] epilogue -> MMA    (4 arrivals: one per epilogue warp)
   uint64_t* hi_full = bars + 12;    // [4] TMA -> splitters + MMA   (1 arrival + the boxes' bytes: hi image landed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  volatile int* tile_ring = reinterpret_cast<volatile int*>(bars + 18);   // [32] tiles, [1] published, [8] read by epilogue warp w
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   AST_TIMELINE_STAMP(cqt, blockIdx.x, 0);
@@ -339,6 +394,7 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
       umma::mbar_init(acc_full + i, 1);
       umma::mbar_init(acc_empty + i, 4);
     }
+    for (int i = 0; i < 9; ++i) tile_ring[kTileRing + i] = 0;
   }
   umma::fence_proxy_async_smem();
   umma::fence_before_thread_sync();
@@ -350,6 +406,7 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
   // memset BEFORE the decimator launch, which also orders this kernel after the previous call's kernels).
   if (!p.flags) pdl_wait();
   const int total = p.tiles_per_clip_oct * kOctaves * p.batch;  // gridDim.x <= total
+  const TileSeq seq{tile_ring, total, kTma && p.queue != nullptr};
 
   if (warp < kProducerWarps) {
     // ================================================================= producers
@@ -453,7 +510,7 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
       // pass, no index algebra.  Only a block that reaches the clip's end (or the end of what the tensor map covers)
       // needs its tail chunks re-read with the bounds applied; those are patched in the hi image as well.
       int item = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int k = 0, tile; (tile = seq.get(k)) < total; ++k) {
         int b, oct, t0;
         decode_tile(p, tile, b, oct, t0);
         if (tile_dead(p, b, t0)) continue;
@@ -544,7 +601,8 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
       for (int i = 0; i < kOctaves; ++i) umma::prefetch_tensormap(&p.maps[i]);
       unsigned stages_complete = 0;
       int item = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      TileFetcher fetch{seq, p.queue, 0, false, 4 * kEpiGroups};
+      for (int k = 0, tile; (tile = fetch.peek(k)) < total; ++k) {
         int b, oct, t0;
         decode_tile(p, tile, b, oct, t0);
         if (tile_dead(p, b, t0)) continue;
@@ -554,9 +612,10 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
         const long long len0 = p.lengths ? p.lengths[b] : p.max_samples;
         const int len = (int)((len0 + (1LL << oct) - 1) >> oct);
         // one thread asks L2 for the signal span of the tile after next, so its box finds it there
-        if (tile + 2 * (int)gridDim.x < total && !(p.debug & 8)) {
+        const int tile2 = fetch.peek(k + 2);
+        if (tile2 < total && !(p.debug & 8)) {
           int b2, oct2, t2;
-          decode_tile(p, tile + 2 * gridDim.x, b2, oct2, t2);
+          decode_tile(p, tile2, b2, oct2, t2);
           const long long len2 = ((p.lengths ? p.lengths[b2] : p.max_samples) + (1LL << oct2) - 1) >> oct2;
           const float* x2 = oct2 == 0 ? p.wave + (long long)b2 * p.wave_stride
                                       : p.ws + (long long)b2 * p.ws_clip_stride + p.oct_off[oct2];
@@ -628,7 +687,7 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
     const uint32_t idesc64 = umma::instr_desc_tf32(kM, 2 * kN), idesc32 = umma::instr_desc_tf32(kM, kN);
     const uint32_t b_addr = umma::smem_u32(b_img);
     int item = 0, n_tile = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    for (int k = 0, tile; (tile = seq.get(k)) < total; ++k) {
       int b, oct, t0;
       decode_tile(p, tile, b, oct, t0);
       if (kTma && tile_dead(p, b, t0)) continue;   // n_tile counts the tiles that use an accumulator set
@@ -732,7 +791,8 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
     // The tile's context is loaded BEFORE the wait for its accumulators, so its global loads overlap the wait.
     TileCtx ctx;
     int n_live = 0;
-    for (int n_pos = 0, tile = blockIdx.x; tile < total; tile += gridDim.x, ++n_pos) {
+    for (int n_pos = 0, tile; (tile = seq.get(n_pos)) < total; ++n_pos) {
+      if (seq.dynamic && lane == 0) tile_ring[kTileRing + 1 + (warp - kEpilogueWarp0)] = n_pos;   // entries < n_pos: done with
       bool dead = false;
       if (kTma) {
         int b, oct, t0;
@@ -939,12 +999,19 @@ static bool make_cqt_tensor_maps(CqtTcParams& p, const float* wave, long long wa
 
 int launch_cqt_tc(const ast_plan* plan, const float* wave, const int32_t* lengths, int batch, long long max_samples,
                   long long wave_stride, const float* ws, long long ws_clip_stride, const int* dec_flags, const OutSpec& out,
-                  cudaStream_t st) {
+                  cudaStream_t st, bool tile_queue) {
   CqtTcParams p;
   memset(&p, 0, sizeof(p));
   p.flags = dec_flags;
   p.flag_tiles0 = decimator_tiles_stage0(max_samples);
   p.stage_done = dec_flags ? dec_flags + decimator_stage_done_offset(batch, max_samples) : nullptr;
+  // The tile queue (its counter sits behind the six stage counters and is zeroed with them, decimator_flag_bytes) pays
+  // when this kernel's CTAs start staggered and nothing runs after it: the feature call, where it follows the STFT
+  // (0.2850 -> 0.2669 ms per 64 clips).  Where it runs into the decimator's tail and the STFT follows it (statistics
+  // call, AST_FEATURE_ORDER=dcs) round-robin lists are better (statistics call 0.2993 vs 0.3067 ms): early CTAs would
+  // draw the low octaves' tiles while the decimator's chain stages are still producing them.
+  p.queue = tile_queue && dec_flags && !getenv("AST_CQT_STATIC")
+                ? const_cast<int*>(dec_flags) + decimator_stage_done_offset(batch, max_samples) + (kOctaves - 1) : nullptr;
   for (int s = 0; s < kOctaves - 1; ++s) p.stage_tiles[s] = decimator_tiles_of_stage(max_samples, s) * batch;
   p.dec_tile_outputs = decimator_tile_outputs();
   p.wave = wave;

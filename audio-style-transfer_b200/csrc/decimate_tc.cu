@@ -581,6 +581,18 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_kernel(const De
 // largest magnitude (producers: register max -> redux -> shared atomicMax -> one named barrier per tile) so that it lies
 // in [2^8, 2^9); residuals that fall into FP16's subnormal range are then below 2^-33 of the tile's largest sample.  The
 // epilogue multiplies the accumulator by 2^(-k-15).
+// Co-residency with the STFT (diagnostic, -DAST_DEC_H_REGS=96 and AST_DEC_CARVEOUT=100): the register file is split over
+// the four schedulers, 16 K registers each, and the fullest of them carries four of this kernel's 14 warps, so one 4-warp
+// STFT CTA (128 registers) fits next to this kernel only at <= 96 registers per thread here (104 leaves 16 K registers free
+// in total and still never co-schedules), and only if the whole unified array is configured as shared memory (the driver's
+// choice for one 188 KB CTA is 196 KB).  Measured on B200 with the STFT launched right behind this kernel: 148 + 148 CTAs
+// are resident from the start, each STFT CTA then takes 46 us instead of 30, this kernel's bulk phase 50 -> 62 us and its
+// chain 85 -> 116 us (28 KB of L1, shared LSU / issue slots): feature step 0.2743 -> 0.2823 ms.  Kept off.
+#ifdef AST_DEC_H_REGS
+#define AST_DEC_H_BOUNDS __maxnreg__(AST_DEC_H_REGS)
+#else
+#define AST_DEC_H_BOUNDS __launch_bounds__(dtc::kThreads, 1)
+#endif
 namespace dth {
 using dtc::kM; using dtc::kN; using dtc::kP; using dtc::kRS; using dtc::kGroupValid; using dtc::kGroups; using dtc::kRowsOut;
 using dtc::kSlices; using dtc::kProducers; using dtc::kEpilogueWarp0; using dtc::kMmaWarp; using dtc::kPublishWarp;
@@ -595,7 +607,7 @@ constexpr int kStripRow0 = 56;                 // strip row of (n = 0, gs = 0): 
 constexpr int kStripBytes = 2 * kStripRows * 16;
 constexpr int kTapShift = 15;                  // taps are staged as g * 2^15 (largest tap ~ 0.65)
 constexpr int kChunksPerThread = kM * kSliceChunks / kProducerGroup;   // 4 shared-memory chunks (8 samples each) per slice
-constexpr size_t kSmem = 4 * kTileBytes + 2 * kStripBytes + sizeof(float) * kEpiFloats + 256 + 128 * 64;   // + the tile table
+constexpr size_t kSmem = 4 * kTileBytes + 2 * kStripBytes + sizeof(float) * kEpiFloats + 256 + 64 * 48;   // 191 744 B   // + the tile table
 }  // namespace dth
 
 __host__ __device__ constexpr uint32_t instr_desc_f16(int m, int n) {   // kind::f16, A = B = FP16, FP32 accumulate, K-major
@@ -647,7 +659,7 @@ __device__ __forceinline__ int dth_tile_at(const DecimateTcParams& p, const DthL
   const int ord = ii / p.tiles_per_clip[s], k = ii - ord * p.tiles_per_clip[s];
   return p.tile_prefix[s] + (l.j + ord * p.tail_ctas) * p.tiles_per_clip[s] + k;
 }
-constexpr int kDthTableCap = 128;   // decoded tiles kept in shared memory (6 KB); longer lists decode the rest on the fly
+constexpr int kDthTableCap = 64;    // decoded tiles kept in shared memory (3 KB); longer lists decode the rest on the fly
 struct DthWalk {
   const DecimateTcParams& p;
   DthList l;
@@ -695,7 +707,7 @@ __device__ __forceinline__ void dth_split4(const float4& a, float scale, uint2& 
   lo = make_uint2(l[0], l[1]);
 }
 
-__global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_h_kernel(const DecimateTcParams p) {
+__global__ void AST_DEC_H_BOUNDS decimate2_tc_h_kernel(const DecimateTcParams p) {
   using namespace dth;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   AST_TIMELINE_STAMP(dec, blockIdx.x, 0);
@@ -716,7 +728,7 @@ __global__ void __launch_bounds__(dtc::kThreads, 1) decimate2_tc_h_kernel(const 
   unsigned int* stored_count = reinterpret_cast<unsigned int*>(bars + 20);   // [4]: one per epilogue warp
   unsigned int* tile_max = reinterpret_cast<unsigned int*>(bars + 16);   // [3] bits of the largest |sample| of tiles n, n + 1, n + 2
   float* tile_inv = reinterpret_cast<float*>(bars + 18);                 // [4] 2^(-k - 15) of the last four tiles
-  DtcTile* table = reinterpret_cast<DtcTile*>(bars + 32);                // [128] the CTA's first tiles, decoded once
+  DtcTile* table = reinterpret_cast<DtcTile*>(bars + 32);                // [64] the CTA's first tiles, decoded once
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   for (int i = tid; i < kStripBytes / 16; i += kThreads) {
@@ -989,6 +1001,8 @@ void set_decimator_half(int on) { g_dec_half = on; }
 int decimate_init() {
   AST_CUDA_TRY(cudaFuncSetAttribute(decimate2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dtc::kSmem));
   AST_CUDA_TRY(cudaFuncSetAttribute(decimate2_tc_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dth::kSmem));
+  if (const char* env = getenv("AST_DEC_CARVEOUT"))   // diagnostic (co-residency experiment above): shared-memory share, %
+    AST_CUDA_TRY(cudaFuncSetAttribute(decimate2_tc_h_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(env)));
   return AST_OK;
 }
 
@@ -1059,7 +1073,8 @@ size_t decimator_flag_bytes(int batch, long long max_samples) {
   const long long rows = (octave_len(max_samples, 1) + dtc::kP - 1) / dtc::kP;
   const long long tiles0 = (rows + dtc::kRowsOut - 1) / dtc::kRowsOut;
   // per-tile counters [stage][clip][tile], then one finished-tile counter per stage
-  return sizeof(int) * ((size_t)kDecStages * (size_t)(batch > 0 ? batch : 1) * (size_t)(tiles0 > 0 ? tiles0 : 1) + kDecStages);
+  // ... and one more int: the CQT projection's tile queue (cqt_tc.cu), zeroed with the rest
+  return sizeof(int) * ((size_t)kDecStages * (size_t)(batch > 0 ? batch : 1) * (size_t)(tiles0 > 0 ? tiles0 : 1) + kDecStages + 1);
 }
 long long decimator_stage_done_offset(int batch, long long max_samples) {
   return (long long)kDecStages * (batch > 0 ? batch : 1) * decimator_tiles_stage0(max_samples);

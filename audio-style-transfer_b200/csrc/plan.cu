@@ -351,6 +351,7 @@ int ast_plan_create(const ast_config* cfg, ast_plan** out) {
   if (rc == AST_OK) rc = decimate_init();
   if (rc == AST_OK) rc = cqt_tc_init();
   if (const char* env = std::getenv("AST_OVERLAP")) set_overlap_streams(std::strcmp(env, "0") != 0);
+  if (const char* env = std::getenv("AST_FEATURE_ORDER")) set_stft_second(std::strcmp(env, "dcs") != 0);
   if (const char* env = std::getenv("AST_CQT"))  // diagnostic A/B switch: "fma" selects the FMA-pipe projection
     set_tc_cqt(std::strcmp(env, "fma") != 0);
   if (const char* env = std::getenv("AST_DECIMATOR")) {  // diagnostic A/B switch: "fma" selects the FMA-pipe kernel, "tf32" the TF32-split tensor kernel
