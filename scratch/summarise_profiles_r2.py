@@ -15,6 +15,9 @@ json.dump({"ours": d, "reference": ref, "commit": head}, open(f"{ROOT}/profiles/
 def short(name):
     return name.split("(")[0].replace("ast::", "").replace("void ", "")
 
+def canon(name):   # the FP16-split decimator is bench.py's / traffic.json's "decimate2_tc_kernel" (the library's profile span)
+    return name.replace("decimate2_tc_h_kernel", "decimate2_tc_kernel")
+
 rows = list(csv.reader(open(f"{g}/r2_launches.csv")))
 h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
 hdr = rows[h]
@@ -22,12 +25,12 @@ ki, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index(
 L = [(short(r[ki]), r[gi], r[bi], float(r[vi].replace(",", "")) / 1000.0) for r in rows[h + 2:] if len(r) > vi]
 out = ["# ncu --metrics gpu__time_duration.sum --clock-control none -c 80: python scratch/prof_step.py --steps 1 --warmup 1 --legs features,istft,stats",
        f"# commit {head}; per-launch device time in us (cold cache, serialised, programmatic overlap off under the profiler: compare SHARES)",
-       "# B200, 64 clips x 10 s: two feature calls (prologue, decimator, CQT projection, STFT), two iSTFT calls, two statistics calls",
+       "# B200, 64 clips x 10 s: two feature calls (prologue, decimator, STFT, CQT projection), two iSTFT calls, two statistics calls (decimator, STFT, CQT projection, finalise, accumulate)",
        "# kernel | grid | block | us"]
 out += [f"{n[:50]:50s} {gr:14s} {bl:12s} {us:9.2f}" for n, gr, bl, us in L]
 agg = collections.defaultdict(list)
 for n, gr, bl, us in L:
-    agg[n].append(us)
+    agg[canon(n)].append(us)
 out.append("# ---- per kernel over all captured launches: n, mean us")
 out += [f"{k[:50]:50s} n={len(v):3d} mean={sum(v) / len(v):9.2f}" for k, v in agg.items()]
 step = {k: sum(v) / len(v) for k, v in agg.items() if k in ("stft_kernel<0>", "decimate2_tc_kernel", "cqt_tc_kernel<1>")}
@@ -59,11 +62,11 @@ traffic, seen, mode = {}, collections.Counter(), "features"
 mul = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}
 for r in rows[2:]:
     dd, u = dict(zip(hdr, r)), dict(zip(hdr, units))
-    name = short(dd["Kernel Name"])
-    if name == "stft_kernel<1>":
-        mode = "stats"
+    name = canon(short(dd["Kernel Name"]))
     if name == "istft_kernel":
         mode = "istft"
+    elif mode == "istft" and name.startswith("decimate2"):   # the statistics calls follow the iSTFT calls
+        mode = "stats"
     key = name if mode != "stats" or name == "stats_finalize_clips_kernel" else name + " [statistics call]"
     seen[key] += 1
     if seen[key] != 2 and not (seen[key] == 1 and key not in traffic and False):
