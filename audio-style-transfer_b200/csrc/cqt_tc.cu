@@ -304,27 +304,38 @@ __device__ __noinline__ void issue_block_any(int oct, uint32_t a_hi_addr, uint32
 // the next tile number from a global counter (tiles are numbered heaviest octave first) and publishes it in a small
 // shared-memory ring the other roles read; total marks the end.
 constexpr int kTileRing = 32;   // entries; the TMA thread is at most ~ 7 tiles ahead of the epilogue (4 stages + 2 accumulator sets)
+// An entry carries its own validity: (lap + 1) << 24 | tile, lap = k / kTileRing - ONE store publishes it (a separate
+// "entries published" word would need a fence between the two stores, and a fence in the TMA thread waits for whatever
+// that thread has in flight).  Tile numbers stay below 2^24 (65 535 clips x 49 tiles).
+template <bool kQueue>
 struct TileSeq {
-  volatile int* ring;   // [kTileRing] tiles, [kTileRing] = number of entries published
+  volatile int* ring;   // [kTileRing] entries (zero: never valid), [kTileRing + 1 + w]: positions epilogue warp w has read
   int total;
-  bool dynamic;
+  static constexpr bool dynamic = kQueue;   // compile time: the kernel is sensitive to its code size (instruction fetches)
   __device__ __forceinline__ int get(int k) const {
     if (!dynamic) {
       const long long t = (long long)blockIdx.x + (long long)k * gridDim.x;
       return t < total ? (int)t : total;
     }
-    while (ring[kTileRing] <= k) __nanosleep(20);
-    return ring[k & (kTileRing - 1)];
+    const int tag = (k / kTileRing + 1) & 0x7F;
+    int e;
+    while (((e = ring[k & (kTileRing - 1)]) >> 24) != tag) __nanosleep(20);
+    return e & 0xFFFFFF;
   }
 };
+template <bool kQueue>
 struct TileFetcher {   // the TMA thread only
-  TileSeq seq;
+  TileSeq<kQueue> seq;
   int* queue;
   int fetched;
   bool ended;
   int n_epi;   // epilogue warps: ring[kTileRing + 1 + w] = positions warp w has read
+  // One draw is always in flight: the atomic's round trip (~ 1 000 cycles; 21 tiles per CTA: 10 us of this thread's
+  // time when each draw was awaited on the spot) overlaps this thread's work on the tiles drawn before it.
+  int inflight;
+  bool have_inflight;
   __device__ __forceinline__ void ensure(int upto) {   // entries 0 .. upto are published (or the end marker is)
-    while (seq.dynamic && fetched <= upto && !ended) {
+    while (kQueue && fetched <= upto && !ended) {
       // Dead tiles (ragged batch) cost this thread nothing but the epilogue a tile of zero rows, so it could run any
       // distance ahead: an entry is overwritten only when every epilogue warp - the last readers - is past it.  (The
       // epilogue never waits for a tile this thread has not issued yet: it is behind, so this cannot deadlock.)
@@ -337,23 +348,24 @@ struct TileFetcher {   // the TMA thread only
         if (fetched - slowest < kTileRing - 1) break;
         __nanosleep(100);
       }
-      int t = atomicAdd(queue, 1);
+      int t = have_inflight ? inflight : atomicAdd(queue, 1);
+      have_inflight = false;
       if (t >= seq.total) t = seq.total, ended = true;
-      seq.ring[fetched & (kTileRing - 1)] = t;
-      __threadfence_block();
-      seq.ring[kTileRing] = ++fetched;
+      seq.ring[fetched & (kTileRing - 1)] = (((fetched / kTileRing + 1) & 0x7F) << 24) | t;
+      ++fetched;
+      if (!ended) inflight = atomicAdd(queue, 1), have_inflight = true;   // (every number drawn is published by a later call)
     }
   }
   __device__ __forceinline__ int peek(int k) {   // tile k if there is one, else total
-    if (!seq.dynamic) return seq.get(k);
+    if (!kQueue) return seq.get(k);
     ensure(k);
-    return k < fetched ? seq.ring[k & (kTileRing - 1)] : seq.total;
+    return k < fetched ? (seq.ring[k & (kTileRing - 1)] & 0xFFFFFF) : seq.total;
   }
 };
 
 AST_TIMELINE_DEFINE(cqt)
 
-template <bool kTma>
+template <bool kTma, bool kQueue>
 __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads, 1)
     cqt_tc_kernel(const __grid_constant__ CqtTcParams p) {
   using namespace cqt_tc;
@@ -375,7 +387,7 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
   uint64_t* acc_empty = bars + 10;  // [2] epilogue -> MMA    (4 arrivals: one per epilogue warp)
   uint64_t* hi_full = bars + 12;    // [4] TMA -> splitters + MMA   (1 arrival + the boxes' bytes: hi image landed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  volatile int* tile_ring = reinterpret_cast<volatile int*>(bars + 18);   // [32] tiles, [1] published, [8] read by epilogue warp w
+  volatile int* tile_ring = reinterpret_cast<volatile int*>(bars + 18);   // [32] entries, [1] unused, [8] read by epilogue warp w
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   AST_TIMELINE_STAMP(cqt, blockIdx.x, 0);
@@ -394,7 +406,7 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
       umma::mbar_init(acc_full + i, 1);
       umma::mbar_init(acc_empty + i, 4);
     }
-    for (int i = 0; i < 9; ++i) tile_ring[kTileRing + i] = 0;
+    for (int i = 0; i < kTileRing + 9; ++i) tile_ring[i] = 0;
   }
   umma::fence_proxy_async_smem();
   umma::fence_before_thread_sync();
@@ -406,7 +418,7 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
   // memset BEFORE the decimator launch, which also orders this kernel after the previous call's kernels).
   if (!p.flags) pdl_wait();
   const int total = p.tiles_per_clip_oct * kOctaves * p.batch;  // gridDim.x <= total
-  const TileSeq seq{tile_ring, total, kTma && p.queue != nullptr};
+  const TileSeq<kQueue> seq{tile_ring, total};
 
   if (warp < kProducerWarps) {
     // ================================================================= producers
@@ -601,7 +613,7 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
       for (int i = 0; i < kOctaves; ++i) umma::prefetch_tensormap(&p.maps[i]);
       unsigned stages_complete = 0;
       int item = 0;
-      TileFetcher fetch{seq, p.queue, 0, false, 4 * kEpiGroups};
+      TileFetcher<kQueue> fetch{seq, p.queue, 0, false, 4 * kEpiGroups, 0, false};
       for (int k = 0, tile; (tile = fetch.peek(k)) < total; ++k) {
         int b, oct, t0;
         decode_tile(p, tile, b, oct, t0);
@@ -792,7 +804,7 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
     TileCtx ctx;
     int n_live = 0;
     for (int n_pos = 0, tile; (tile = seq.get(n_pos)) < total; ++n_pos) {
-      if (seq.dynamic && lane == 0) tile_ring[kTileRing + 1 + (warp - kEpilogueWarp0)] = n_pos;   // entries < n_pos: done with
+      if (kQueue && lane == 0) tile_ring[kTileRing + 1 + (warp - kEpilogueWarp0)] = n_pos;   // entries < n_pos: done with
       bool dead = false;
       if (kTma) {
         int b, oct, t0;
@@ -938,8 +950,9 @@ extern "C" int ast_debug_cqt_trace(long long* host) {
 #endif
 
 int cqt_tc_init() {
-  AST_CUDA_TRY(cudaFuncSetAttribute(cqt_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cqt_tc::kSmemTma));
-  AST_CUDA_TRY(cudaFuncSetAttribute(cqt_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cqt_tc::kSmem));
+  AST_CUDA_TRY(cudaFuncSetAttribute(cqt_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cqt_tc::kSmemTma));
+  AST_CUDA_TRY(cudaFuncSetAttribute(cqt_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cqt_tc::kSmemTma));
+  AST_CUDA_TRY(cudaFuncSetAttribute(cqt_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cqt_tc::kSmem));
   return AST_OK;
 }
 
@@ -1010,7 +1023,7 @@ int launch_cqt_tc(const ast_plan* plan, const float* wave, const int32_t* length
   // (0.2850 -> 0.2669 ms per 64 clips).  Where it runs into the decimator's tail and the STFT follows it (statistics
   // call, AST_FEATURE_ORDER=dcs) round-robin lists are better (statistics call 0.2993 vs 0.3067 ms): early CTAs would
   // draw the low octaves' tiles while the decimator's chain stages are still producing them.
-  p.queue = tile_queue && dec_flags && !getenv("AST_CQT_STATIC")
+  p.queue = (tile_queue || getenv("AST_CQT_QUEUE_ALWAYS")) && dec_flags && !getenv("AST_CQT_STATIC")
                 ? const_cast<int*>(dec_flags) + decimator_stage_done_offset(batch, max_samples) + (kOctaves - 1) : nullptr;
   for (int s = 0; s < kOctaves - 1; ++s) p.stage_tiles[s] = decimator_tiles_of_stage(max_samples, s) * batch;
   p.dec_tile_outputs = decimator_tile_outputs();
@@ -1042,12 +1055,15 @@ int launch_cqt_tc(const ast_plan* plan, const float* wave, const int32_t* length
   if (2LL * p.slots * out.f_row * (out.layout == AST_LAYOUT_FLAT ? 1 : 2) >= (1LL << 31))
     return fail(AST_ERR_INVALID_ARG, "clip too long for the CQT epilogue's 32-bit in-clip offsets");
   long long ctas = (long long)p.tiles_per_clip_oct * kOctaves * batch;
+  if (ctas >= (1LL << 24)) p.queue = nullptr;   // ring entries carry 24-bit tile numbers
   if (ctas > plan->sm_count) ctas = plan->sm_count;  // persistent: one CTA per SM
   ProfileSpan span("cqt_tc_kernel", st);
-  if (p.use_tma)
-    AST_CUDA_TRY(launch_with_pdl(cqt_tc_kernel<true>, dim3((unsigned)ctas), cqt_tc::kThreadsTma, cqt_tc::kSmemTma, st, p));
+  if (p.use_tma && p.queue)
+    AST_CUDA_TRY(launch_with_pdl(cqt_tc_kernel<true, true>, dim3((unsigned)ctas), cqt_tc::kThreadsTma, cqt_tc::kSmemTma, st, p));
+  else if (p.use_tma)
+    AST_CUDA_TRY(launch_with_pdl(cqt_tc_kernel<true, false>, dim3((unsigned)ctas), cqt_tc::kThreadsTma, cqt_tc::kSmemTma, st, p));
   else
-    AST_CUDA_TRY(launch_with_pdl(cqt_tc_kernel<false>, dim3((unsigned)ctas), cqt_tc::kThreads, cqt_tc::kSmem, st, p));
+    AST_CUDA_TRY(launch_with_pdl(cqt_tc_kernel<false, false>, dim3((unsigned)ctas), cqt_tc::kThreads, cqt_tc::kSmem, st, p));
   return AST_OK;
 }
 
