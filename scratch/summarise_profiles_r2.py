@@ -33,7 +33,7 @@ for n, gr, bl, us in L:
     agg[canon(n)].append(us)
 out.append("# ---- per kernel over all captured launches: n, mean us")
 out += [f"{k[:50]:50s} n={len(v):3d} mean={sum(v) / len(v):9.2f}" for k, v in agg.items()]
-step = {k: sum(v) / len(v) for k, v in agg.items() if k in ("stft_kernel<0>", "decimate2_tc_kernel", "cqt_tc_kernel<1>")}
+step = {k: sum(v) / len(v) for k, v in agg.items() if k in ("stft_kernel<0>", "decimate2_tc_kernel", "cqt_tc_kernel<1>", "cqt_tc_kernel<1, 1>", "cqt_tc_kernel<1, 0>")}
 tot = sum(step.values())
 out.append("# ---- share of the feature step (serialised): " + ", ".join(f"{k} {100 * v / tot:.1f}%" for k, v in step.items()))
 kb = d["roofline"]["kernels"]
@@ -84,7 +84,7 @@ open(f"{ROOT}/profiles/{tag}_ncu_full.txt", "w").write("\n".join(txt))
 stats_traffic = sum(v for k, v in traffic.items() if "[statistics call]" in k or k == "stats_finalize_clips_kernel")
 json.dump({"how": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full --clock-control none, 64 clips x 10 s, cold L2 per replay",
            "commit": head, "source": f"gpurun_out/r2_full.ncu-rep summarised in profiles/{tag}_ncu_full.txt",
-           "dram_bytes_per_launch": {k.replace("<0>", "").replace("<1>", "") if "[" not in k else k: v for k, v in traffic.items()},
+           "dram_bytes_per_launch": {k.split("<")[0] if "[" not in k else k: v for k, v in traffic.items()},
            "statistics_call_dram_bytes_per_clip": stats_traffic / 64.0,
            "algorithmic_bytes_per_launch": {"stft_kernel": 64 * (882000 + 4711392), "cqt_tc_kernel": 64 * (1764228 + 771616),
                                             "istft_kernel": 64 * 5591008, "decimate2_tc_kernel": 64 * 2604672,
