@@ -603,3 +603,22 @@ def test_cqt_is_homogeneous_over_the_float_range(fe, gain):
     # the quiet half on its own terms: relative to ITS largest value (frames well inside it)
     q0 = 30000 // 256 + 40   # (the lowest octave's filters span 64 frames)
     assert np.abs(got[:, q0:] - base[:, q0:]).max() <= 2e-5 * np.abs(base[:, q0:]).max()
+
+
+@pytest.mark.gpu
+def test_cqt_does_not_depend_on_the_batch_a_clip_travels_in(fe):
+    """The decimator deals its tiles differently with the batch size (chain stages on a few CTAs up to 64 clips, round
+    robin beyond; a CTA's first 64 tiles come from a decoded table in shared memory, later ones are decoded on the
+    fly: 320 full-length clips give a CTA ~ 67) and the CQT projection's CTAs draw their tiles from a queue in the
+    feature call.  None of this may change a single bit of a clip's result: every tile's arithmetic, including its FP16
+    staging scale, depends on the tile alone.  (custom_collate_fn, dataloader.py:123-147, batches clips independently.)"""
+    base = np.stack([synth.clip("piano" if i % 2 == 0 else "violin", 500 + i, 220500) for i in range(4)])
+    gains = np.random.default_rng(3).uniform(0.5, 1.5, 320).astype(np.float32)
+    wave = base[np.arange(320) % 4] * gains[:, None]
+    big = fe.cqt(cuda(wave)).cpu().numpy()
+    for n in (1, 3, 64, 65):
+        small = fe.cqt(cuda(wave[:n])).cpu().numpy()
+        assert np.array_equal(small, big[:n]), n
+    # the fused feature call (queue-fed projection, STFT in between) against the CQT-only call
+    feats, _ = fe.features(cuda(wave[:64]), layout="flat")
+    assert np.array_equal(feats[..., 513:].cpu().numpy(), big[:64])
