@@ -886,36 +886,45 @@ __global__ void AST_DEC_H_BOUNDS decimate2_tc_h_kernel(const DecimateTcParams p)
       if (quad == 0) DTC_STAMP(3, n, 1);
       const float inv = *reinterpret_cast<volatile float*>(tile_inv + (n & 3));
       const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(q * kN);
+      // Eight groups of eight columns, two register sets: the loads of group g + 1 are issued before group g is summed
+      // and staged, so one TMEM round trip is exposed per tile instead of four (tcgen05.wait::ld waits for every
+      // outstanding load, hence "wait, issue the next, work on this one").
+      uint32_t ra[4][8], rb[4][8];
+      auto issue = [&](uint32_t (&r)[4][8], int g) {
+        umma::tmem_ld_32x8_nowait(lane_base + 3 * kP + 8 * g, r[0]);   // d = 0: this row
+        umma::tmem_ld_32x8_nowait(lane_base + 2 * kP + 8 * g, r[1]);   // d = 1: wanted by the row above (lane - 1)
+        umma::tmem_ld_32x8_nowait(lane_base + 1 * kP + 8 * g, r[2]);
+        umma::tmem_ld_32x8_nowait(lane_base + 8 * g, r[3]);
+      };
+      auto finish = [&](const uint32_t (&r)[4][8], int g) {
+        if (p.debug & 1) return;
+        float o[8];
 #pragma unroll
-      for (int cq = 0; cq < kP / 16; ++cq) {
-        uint32_t r0[16], r1[16], r2[16], r3[16];
-        umma::tmem_ld_32x16_nowait(lane_base + 3 * kP + 16 * cq, r0);
-        umma::tmem_ld_32x16_nowait(lane_base + 2 * kP + 16 * cq, r1);
-        umma::tmem_ld_32x16_nowait(lane_base + 1 * kP + 16 * cq, r2);
-        umma::tmem_ld_32x16_nowait(lane_base + 16 * cq, r3);
+        for (int c = 0; c < 8; ++c) {
+          const float s1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[1][c]), 1);
+          const float s2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[2][c]), 2);
+          const float s3 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[3][c]), 3);
+          o[c] = ((__uint_as_float(r[0][c]) + s1) + (s2 + s3)) * inv;
+        }
+        *reinterpret_cast<float4*>(stg + lane * kEpiStride + 8 * g) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(stg + lane * kEpiStride + 8 * g + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      };
+      issue(ra, 0);
+#pragma unroll
+      for (int g = 0; g < kP / 8; g += 2) {
         umma::tmem_wait_ld();
-        float v0[16], v1[16], v2[16], v3[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c)
-          v0[c] = __uint_as_float(r0[c]), v1[c] = __uint_as_float(r1[c]), v2[c] = __uint_as_float(r2[c]), v3[c] = __uint_as_float(r3[c]);
-        if (cq == kP / 16 - 1) {
+        issue(rb, g + 1);
+        finish(ra, g);
+        umma::tmem_wait_ld();
+        if (g + 2 < kP / 8) {
+          issue(ra, g + 2);
+        } else {   // last TMEM read of the tile: hand the accumulator back
           umma::fence_before_thread_sync();
           __syncwarp();
           if (lane == 0) umma::mbar_arrive(acc_empty + q);
           if (quad == 0) DTC_STAMP(3, n, 2);
         }
-        if (p.debug & 1) continue;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const float s1 = __shfl_down_sync(0xffffffffu, v1[c], 1);
-          const float s2 = __shfl_down_sync(0xffffffffu, v2[c], 2);
-          const float s3 = __shfl_down_sync(0xffffffffu, v3[c], 3);
-          v0[c] = ((v0[c] + s1) + (s2 + s3)) * inv;
-        }
-#pragma unroll
-        for (int w = 0; w < 4; ++w)
-          *reinterpret_cast<float4*>(stg + lane * kEpiStride + 16 * cq + 4 * w) =
-              make_float4(v0[4 * w], v0[4 * w + 1], v0[4 * w + 2], v0[4 * w + 3]);
+        finish(rb, g + 1);
       }
       __syncwarp();
       const int j_grp = (t.row0 + kGroupValid * quad) * kP;
