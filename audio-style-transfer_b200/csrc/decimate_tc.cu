@@ -613,16 +613,6 @@ constexpr size_t kSmem = 4 * kTileBytes + 2 * kStripBytes + sizeof(float) * kEpi
 __host__ __device__ constexpr uint32_t instr_desc_f16(int m, int n) {   // kind::f16, A = B = FP16, FP32 accumulate, K-major
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-// non-blocking probe of an mbarrier phase (warp-uniform result: every lane probes)
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done) : "r"(umma::smem_u32(bar)), "r"(parity) : "memory");
-  return __all_sync(0xffffffffu, done != 0);
-}
 __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
