@@ -389,14 +389,17 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
   uint64_t* acc_empty = bars + 10;  // [2] epilogue -> MMA    (4 arrivals: one per epilogue warp)
   uint64_t* hi_full = bars + 12;    // [4] TMA -> splitters + MMA   (1 arrival + the boxes' bytes: hi image landed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* b_full = bars + 17;     // TMA variants: the B images have landed
   volatile int* tile_ring = reinterpret_cast<volatile int*>(bars + 18);   // [32] entries, [1] unused, [8] read by epilogue warp w
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   AST_TIMELINE_STAMP(cqt, blockIdx.x, 0);
   pdl_launch_dependents();
-  // B images: resident for the CTA's lifetime
-  for (int i = tid; i < kBFloats / 4; i += (int)blockDim.x)
-    reinterpret_cast<float4*>(b_img)[i] = __ldg(reinterpret_cast<const float4*>(p.bmat) + i);
+  // B images: resident for the CTA's lifetime.  TMA variants: one 64 KB bulk copy, started below as soon as its barrier
+  // exists, lands while the TMEM is allocated and the first boxes are requested; the MMA warp waits for it once.
+  if (!kTma)
+    for (int i = tid; i < kBFloats / 4; i += (int)blockDim.x)
+      reinterpret_cast<float4*>(b_img)[i] = __ldg(reinterpret_cast<const float4*>(p.bmat) + i);
   if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, kTmemCols);
   if (tid == 0) {
     for (int i = 0; i < kNStages; ++i) {
@@ -409,6 +412,12 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
       umma::mbar_init(acc_empty + i, 4);
     }
     for (int i = 0; i < kTileRing + 9; ++i) tile_ring[i] = 0;
+    if (kTma) {
+      umma::mbar_init(b_full, 1);
+      umma::mbar_arrive_expect_tx(b_full, (uint32_t)(kBFloats * 4));
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(umma::smem_u32(b_img)), "l"(p.bmat), "r"((uint32_t)(kBFloats * 4)), "r"(umma::smem_u32(b_full)) : "memory");
+    }
   }
   umma::fence_proxy_async_smem();
   umma::fence_before_thread_sync();
@@ -707,6 +716,7 @@ __global__ void __launch_bounds__(kTma ? cqt_tc::kThreadsTma : cqt_tc::kThreads,
     // ================================================================= MMA issue
     const uint32_t idesc64 = umma::instr_desc_tf32(kM, 2 * kN), idesc32 = umma::instr_desc_tf32(kM, kN);
     const uint32_t b_addr = umma::smem_u32(b_img);
+    if (kTma) umma::mbar_wait(b_full, 0);
     int item = 0, n_tile = 0;
     for (int k = 0, tile; (tile = seq.get(k)) < total; ++k) {
       int b, oct, t0;
