@@ -232,20 +232,21 @@ int ast_features_forward(const ast_plan* plan, const float* wave, const int32_t*
     if (rc != AST_OK) return rc;
     return launch_cqt(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, use_tc_decimator() ? w.dec_flags : nullptr, oq, st);
   }
-  // One stream, three programmatic dependent launches: decimator cascade -> CQT projection (runs into the decimator's
-  // tail, block by block behind its completion counters) -> STFT (never waits: disjoint output columns; its small CTAs
-  // fill the SMs as the persistent CQT CTAs retire).  The memset inside launch_decimate_cascade is an ordinary stream
-  // operation, so nothing of this call starts before the previous call's kernels have finished.
+  // One stream, three programmatic dependent launches behind the prologue ("Launch structure").
+  // Default order: decimator cascade -> STFT -> CQT projection (below); AST_FEATURE_ORDER=dcs keeps the earlier order
+  // decimator -> CQT projection -> STFT (further below).  When the call is not chained, the memset inside
+  // launch_decimate_cascade is an ordinary stream operation, so nothing starts before the previous call has finished.
   rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, st,
                                /*flags_zeroed=*/chained);
   if (rc != AST_OK) return rc;
   if (chained && g_stft_second) {
-    // decimator -> STFT -> CQT projection.  The FP16-split decimator leaves 16 K registers and 35 KB of shared memory
-    // of every SM free: exactly one 4-warp STFT CTA, so the STFT starts UNDER the decimator (tensor pipe there, FP32 / LSU
-    // pipes here), takes the SMs over as the decimator's CTAs retire, and the CQT projection's persistent CTAs (a whole SM
-    // each) start as the STFT's last wave drains.  The STFT's last CTA waits for its programmatic primary (now the
-    // decimator), every CQT CTA for its primary (now the STFT) before it exits: "the call's last kernel is complete"
-    // still means the whole call is.
+    // decimator -> STFT -> CQT projection.  The STFT waits for nothing (it reads the waveform and writes its own
+    // columns): its small CTAs take the SMs over as the decimator's persistent CTAs retire (the 32 chain CTAs last), and
+    // the projection's persistent CTAs (a whole SM each) start as the STFT's last wave drains, drawing their tiles from a
+    // queue so that they end together.  (With the default build the STFT does not co-reside with the decimator: that
+    // needs the full shared-memory carve-out and a 96-register decimator, was measured and is slower - DESIGN.md section 5.)
+    // The STFT's last CTA waits for its programmatic primary (the decimator), every CQT CTA for its primary (the STFT)
+    // before it exits: "the call's last kernel is complete" still means the whole call is.
     rc = launch_stft(plan, wave, lengths, batch, max_samples, wave_stride, o, st, 0, /*pdl=*/true,
                      reinterpret_cast<unsigned int*>(w.dec_flags + tail_counter_index(batch, max_samples)), stat4, stat4_stride);
     if (rc != AST_OK) return rc;
@@ -323,10 +324,9 @@ int ast_stats_accumulate(const ast_plan* plan, const float* wave, const int32_t*
   OutSpec o = make_out(plan, nullptr, AST_LAYOUT_FLAT, t_dim, kFTotal, 0);
   const int stft_tiles = stft_tiles_per_clip(plan, batch, t_dim, /*stats_mode=*/true);
   if (stft_tiles > stats_stft_tiles_max(max_samples)) return fail(AST_ERR_WORKSPACE, "internal: statistics tile bound exceeded");
-  // same order as the feature call: decimator -> CQT projection (runs into the decimator's tail) -> STFT as the
-  // projection's programmatic dependent (it waits for nothing: it reads the waveform and writes its own partials, and
-  // its CTAs fill the SMs as the persistent CQT CTAs retire).  The finalise kernel is an ordinary launch: it starts
-  // when everything before it on the stream has completed.
+  // same order as the feature call: decimator -> STFT (statistics mode; it waits for nothing: it reads the waveform and
+  // writes its own partials) -> CQT projection; AST_STATS_ORDER_DCS keeps the earlier order with the STFT last.  The
+  // finalise kernel is an ordinary launch: it starts when everything before it on the stream has completed.
   const long long ws_stride = cqt_ws_clip_stride(max_samples);
   rc = launch_decimate_cascade(plan, wave, lengths, batch, max_samples, wave_stride, w.octaves, ws_stride, w.dec_flags, st);
   if (rc != AST_OK) return rc;

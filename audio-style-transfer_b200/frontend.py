@@ -400,14 +400,27 @@ class FrontEnd:
         counts = torch.zeros((n_groups,), dtype=torch.float64, device=self.device)
         return acc, counts
 
+    def _check_accumulator(self, acc: torch.Tensor, counts: torch.Tensor, f_dim: int = F_TOTAL) -> None:
+        # the kernels add into these buffers through raw pointers: a host tensor or another dtype would be a wild write
+        if (acc.ndim != 4 or tuple(acc.shape[1:]) != (2, 2, f_dim) or acc.dtype != torch.float64 or acc.device != self.device
+                or not acc.is_contiguous()):
+            raise ValueError(f"acc must be a contiguous float64 (G, 2, 2, {f_dim}) tensor on {self.device} "
+                             "(new_stats_accumulator)")
+        if (tuple(counts.shape) != (acc.shape[0],) or counts.dtype != torch.float64 or counts.device != self.device
+                or not counts.is_contiguous()):
+            raise ValueError(f"counts must be a contiguous float64 ({acc.shape[0]},) tensor on {self.device}")
+
     def stats_accumulate(self, wave: torch.Tensor, acc: torch.Tensor, counts: torch.Tensor,
                          lengths: Optional[torch.Tensor] = None, group_ids: Optional[torch.Tensor] = None) -> None:
         """Adds the per-clip per-bin mean / unbiased variance of the raw features of ``wave`` into ``acc``
         (``compute_separated_stats.py:16-43``)."""
+        self._check_accumulator(acc, counts)
         wave, lengths = self._wave(wave, lengths)
         B, L = wave.shape
         if group_ids is not None:
             group_ids = group_ids.to(device=self.device, dtype=torch.int32).contiguous()
+            if group_ids.shape != (B,):
+                raise ValueError("group_ids must have one entry per clip")
         nbytes = self.lib.ast_stats_workspace_bytes(self._plan, B, L)
         ws = self._workspace(nbytes)
         with torch.cuda.device(self.device):
@@ -418,7 +431,10 @@ class FrontEnd:
     def stats_accumulate_features(self, feats: torch.Tensor, acc: torch.Tensor, counts: torch.Tensor,
                                   n_frames: Optional[torch.Tensor] = None, group_ids: Optional[torch.Tensor] = None) -> None:
         feats = feats.to(device=self.device, dtype=torch.float32).contiguous()
+        if feats.ndim != 4 or feats.shape[1] != 2:
+            raise ValueError(f"feats must be (B, 2, T, F), got {tuple(feats.shape)}")
         B, _, t_dim, f_dim = feats.shape
+        self._check_accumulator(acc, counts, f_dim)
         if n_frames is not None:
             n_frames = n_frames.to(device=self.device, dtype=torch.int32).contiguous()
         if group_ids is not None:
