@@ -430,6 +430,13 @@ def test_stats_ragged_and_constant(fe):
     acc, counts = fe.new_stats_accumulator(1)
     fe.stats_accumulate_features(feats, acc, counts)
     assert torch.all(acc[0, 0] == 3.0) and torch.all(acc[0, 1] == 0.0) and counts.tolist() == [2.0]
+    # accumulators reach the kernels as raw pointers: anything but the float64 device buffers is refused up front
+    with pytest.raises(ValueError):
+        fe.stats_accumulate(cuda(wave), acc.cpu(), counts)
+    with pytest.raises(ValueError):
+        fe.stats_accumulate(cuda(wave), acc.float(), counts)
+    with pytest.raises(ValueError):
+        fe.stats_accumulate_features(feats, acc, counts.cpu())
 
 
 # ------------------------------------------------------------------------------- full-size properties
