@@ -15,6 +15,7 @@
 // per pair, 16 x 16 x 4, two exchanges, three block barriers per pair) issued ~ 2 800 warp instructions per pair and
 // was issue / latency bound at 0.131 ms per 64 clips; this formulation issues ~ 1 100.
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -47,6 +48,9 @@ struct StftParams {
   int slots;            // frame slots per clip (rows of the output the kernel must cover)
   int pairs_per_clip;   // ceil(slots / 2)
   int iters;            // pairs per warp (consecutive warps of a CTA take consecutive pairs)
+  int taper_from;       // feature mode: grid rows >= taper_from are HALF rows of the last clips (iters / 2 pairs per warp, two
+                        // rows per clip), and after taper_half_rows of those QUARTER rows (iters / 4, four rows per clip): the
+  int taper_half_rows;  // kernel's last CTAs are shorter, so the SMs drain sooner; taper_from >= rows of the grid: off
   const float2* tw32;   // [32][32] W_1024^(n2 k1)
   const float* hann;
   const float4* stat4;  // (-mean_re, -mean_im, rstd_re, rstd_im) per bin, [clip or 0][516]; nullptr: no normalisation
@@ -164,10 +168,24 @@ struct StftStage {
   }
 };
 
+// AST_STFT_EVICT_FIRST: the feature rows are written once and not read again inside the call; marking them evict-first
+// in the L2 leaves the octave signals (113 MB per 64 clips, written by the decimator, read next by the CQT projection)
+// a better chance to stay resident behind the STFT's 300 MB of output.
+#ifndef AST_STFT_EVICT_FIRST
+#define AST_STFT_EVICT_FIRST 0
+#endif
 __device__ __forceinline__ void bulk_store(float* gmem, const float* smem, uint32_t bytes) {
+#if AST_STFT_EVICT_FIRST
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gmem),
+               "r"((uint32_t)__cvta_generic_to_shared(smem)), "r"(bytes), "l"(policy)
+               : "memory");
+#else
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem),
                "r"((uint32_t)__cvta_generic_to_shared(smem)), "r"(bytes)
                : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -328,7 +346,20 @@ __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 3) 
   float* warp_n = reinterpret_cast<float*>(stft_smem + kStftSmem + sizeof(float4) * kStftWarps * kAccStride);
   if (kMode == 0) AST_TIMELINE_STAMP(stft, blockIdx.x + gridDim.x * blockIdx.y, 0);
   pdl_launch_dependents();
-  const int b = blockIdx.y;
+  int b = blockIdx.y, bx = blockIdx.x, iters = p.iters;
+  if (kMode == 0 && b >= p.taper_from) {   // a half or quarter row of one of the last clips (launch_stft)
+    int r = b - p.taper_from;
+    if (r < p.taper_half_rows) {
+      b = p.taper_from + (r >> 1);
+      iters >>= 1;
+      bx += (r & 1) * gridDim.x;
+    } else {
+      r -= p.taper_half_rows;
+      b = p.taper_from + (p.taper_half_rows >> 1) + (r >> 2);
+      iters >>= 2;
+      bx += (r & 3) * gridDim.x;
+    }
+  }
   const int len = (int)(p.lengths ? p.lengths[b] : p.max_samples);
   const int frames_b = num_frames(len);
   const int sections_b = p.out.layout == AST_LAYOUT_SECTIONS ? num_sections(frames_b, p.out.window, p.overlap) : 0;
@@ -361,8 +392,8 @@ __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 3) 
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    const int first = blockIdx.x * p.iters * kStftWarps + warp;
-    if (p.iters > 0 && pf_interior(first)) pf_issue(first), pf_pending = true;
+    const int first = bx * iters * kStftWarps + warp;
+    if (iters > 0 && pf_interior(first)) pf_issue(first), pf_pending = true;
   }
 #endif
 
@@ -380,9 +411,9 @@ __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 3) 
     g_stft_cta_ns[cta_lin_][2] = smid_;
   }
 #endif
-  for (int it = 0; it < p.iters; ++it) {
+  for (int it = 0; it < iters; ++it) {
     STFT_STAMP(0);   // loop overhead / previous pair's tail
-    const int pair = (blockIdx.x * p.iters + it) * kStftWarps + warp;
+    const int pair = (bx * iters + it) * kStftWarps + warp;
     if (pair >= p.pairs_per_clip) break;   // warp-uniform; nothing below synchronises across warps
     const int ta = 2 * pair;
     const bool any_live = ta < frames_b, live_b = ta + 1 < frames_b;
@@ -412,7 +443,7 @@ __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 3) 
           for (int i = 0; i < 40; ++i) xv[i] = __ldg(xp + 32 * i);
         }
 #if AST_STFT_SMEM_PF
-        if (pf_ok && it + 1 < p.iters && pf_interior(pair + kStftWarps)) pf_issue(pair + kStftWarps), pf_pending = true;
+        if (pf_ok && it + 1 < iters && pf_interior(pair + kStftWarps)) pf_issue(pair + kStftWarps), pf_pending = true;
 #endif
 #ifndef AST_STFT_PF
 #define AST_STFT_PF (AST_STFT_SMEM_PF ? 0 : 1)
@@ -420,10 +451,10 @@ __global__ void __launch_bounds__(kStftThreads, kMode == 0 ? AST_STFT_CTAS : 3) 
 #if AST_STFT_PF == 1
         // this warp's next pair starts kStftWarps x 512 samples further; its first 768 samples are being read by the
         // CTA's other warps right now, the last 512 (16 lines) are new: one line per lane into the L1
-        if (it + 1 < p.iters && lane < 16 && (ta + 2 * kStftWarps + 1) * kHop + kNfft / 2 <= len)
+        if (it + 1 < iters && lane < 16 && (ta + 2 * kStftWarps + 1) * kHop + kNfft / 2 <= len)
           asm volatile("prefetch.global.L1 [%0];" ::"l"(xp + 2 * kStftWarps * kHop + 768 - lane + 32 * lane));
 #elif AST_STFT_PF == 2
-        if (it + 1 < p.iters && (ta + 2 * kStftWarps + 1) * kHop + kNfft / 2 <= len) {
+        if (it + 1 < iters && (ta + 2 * kStftWarps + 1) * kHop + kNfft / 2 <= len) {
           const float* xn = xp - lane + 2 * kStftWarps * kHop;
           asm volatile("prefetch.global.L1 [%0];" ::"l"(xn + 32 * lane));
           if (lane < 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(xn + 32 * (32 + lane)));
@@ -640,6 +671,23 @@ static int pick_iters(long long groups_per_clip, int batch, long long slots, int
   return best_it;
 }
 
+// clips whose rows are dealt as half / quarter rows at the end of the grid (launch_stft): none unless the grid runs over
+// several waves of resident CTAs.  Measured on the chained feature call (64 clips x 10 s, 27 CTAs per clip, 592 resident):
+// no taper 0.2563 ms, 8 half 0.2542, 16 half 0.2542, 32 half 0.2555, 8 half + 4 quarter 0.2538, 4 + 2 0.2531, 3 + 2 0.2530,
+// 2 + 1 0.2537 (profiles/r2_v10_stft_taper_ab.txt): the quarter clips' CTAs amount to ~ 0.09 of a wave, the half clips' to ~ 0.18
+static void stft_default_taper(const ast_plan* plan, int batch, int ctas_per_clip, int iters, int* half, int* quarter) {
+  const long long slots = (long long)plan->sm_count * g_stft_ctas_per_sm;
+  *half = *quarter = 0;
+  if ((long long)ctas_per_clip * batch <= slots || ctas_per_clip <= 0) return;
+  const double wave_clips = (double)slots / ctas_per_clip;   // clips whose CTAs fill the machine once
+  int q = iters % 4 == 0 ? (int)(0.09 * wave_clips + 0.5) : 0;
+  int h = (int)(0.18 * wave_clips + 0.5);
+  if (q > batch / 8) q = batch / 8;
+  if (h > batch / 4) h = batch / 4;
+  *half = h;
+  *quarter = q;
+}
+
 int stft_tiles_per_clip(const ast_plan* plan, int batch, int slots, bool stats_mode) {
   const long long pairs = (slots + 1) / 2, groups = (pairs + kStftWarps - 1) / kStftWarps;
   if (groups == 0 || batch == 0) return 0;
@@ -685,6 +733,29 @@ int launch_stft(const ast_plan* plan, const float* wave, const int32_t* lengths,
     }
   p.iters = (int)iters;
   dim3 grid((unsigned)((groups_per_clip + iters - 1) / iters), (unsigned)batch);
+  // Tapered tail (feature mode): the last `taper` clips are dealt as two half rows each, with half the pairs per warp.
+  // CTAs are dispatched in grid order, so these are the kernel's last CTAs: the SMs drain in half the time, and whatever
+  // follows on the stream (the chained call's CQT projection, one persistent CTA per SM that needs the SM empty) starts
+  // sooner - at the fixed cost of a CTA for the extra rows only.
+  int half = 0, quarter = 0;   // clips dealt as half rows, then clips dealt as quarter rows
+  if (!stats_mode && iters >= 2 && iters % 2 == 0) {
+    stft_default_taper(plan, batch, (int)grid.x, (int)iters, &half, &quarter);
+    if (const char* env = getenv("AST_STFT_TAPER")) {   // diagnostic override: "half[,quarter]" clips
+      half = atoi(env), quarter = 0;
+      if (const char* c = strchr(env, ',')) quarter = atoi(c + 1);
+    }
+    if (iters % 4 != 0) half += quarter, quarter = 0;
+    if (half < 0) half = 0;
+    if (quarter < 0) quarter = 0;
+    if (quarter > batch) quarter = batch;
+    if (half + quarter > batch) half = batch - quarter;
+    while (batch + half + 3 * quarter > 65535) {   // rows of the grid
+      if (quarter > 0) --quarter; else --half;
+    }
+  }
+  p.taper_from = batch - half - quarter;
+  p.taper_half_rows = 2 * half;
+  grid.y = (unsigned)(batch + half + 3 * quarter);
   ProfileSpan span("stft_kernel", st);
   if (stats_mode) {
     if ((int)grid.x != tiles) return fail(AST_ERR_INVALID_ARG, "internal: statistics tile count mismatch");
