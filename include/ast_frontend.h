@@ -21,6 +21,9 @@
  *     counters written by other CTAs of the same call; two such grids dispatched interleaved
  *     from different streams could each be partly resident and starve one another (the
  *     bounded waits would then trap).  Copies and every other entry point may overlap freely;
+ *   - a plan lives on ONE device (ast_config.device): ast_plan_create makes that device the calling
+ *     thread's current device and leaves it so; every compute entry point launches on the calling
+ *     thread's current device, which must be the plan's (and the stream's) device;
  *   - float32 data, int32 lengths, row-major contiguous tensors in the reference's layouts.
  *
  * Geometry (fixed by the reference's call sites, utilityFunctions.py:12,39,62):
